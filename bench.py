@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""Throughput benchmark of the Synchformer forward path on B200 (BASELINE.json metric: clips/sec of offset inference).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 64] [--segments 8] [--impl b200|reference]
+
+A step = one pass of the hot path over one batch of synthetic clips (per GPU): raw 16 kHz waveform -> GPU mel front-end,
+fp16 RGB segments -> Motionformer, AST, CLS aggregators, projections, [all-gather of segment features when N > 1],
+sync transformer -> (B, 21) logits.  Workload at N = 1 is BASELINE.json configs[1]: sync.yaml inference, batch 64,
+8 segments / clip, bf16.  Scaling is weak: every rank processes `--batch` clips, `value` = all clips / max-over-ranks time.
+
+Rank 0 prints ONE JSON line (see the keys in main()).  `--impl reference` times the CPU oracle restatement of the reference
+(`oracle/`, "port": the Python reference cannot travel to the GPU box) on the host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+GFLOP_PER_SEGMENT = 408.260            # BASELINE.md §3 (canonical reference op graph, 2 x MAC)
+
+
+def flops_per_clip(S: int) -> float:
+    T = 2 + 14 * S
+    return (S * GFLOP_PER_SEGMENT * 1e9 + 2 * (14 * S) * 768 ** 2 + 3 * (24 * T * 768 ** 2 + 8 * 4 * T * T * 96) + 2 * 768 * 21)
+
+
+def measured_peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(sustained=float(d.get('bf16_tflops_sustained', 1395.6)), burst=float(d.get('bf16_tflops', 1696.6)),
+                    hbm=float(d.get('hbm_gbs', 6445.0)), source='measured (MEASURED_PEAKS.json)')
+    return dict(sustained=1400.0, burst=1590.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index), '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm)}
+
+
+def cpu_oracle_clips_per_sec(S: int, n_clips: int, steps: int, warmup: int):
+    """The reference's algorithm on the host cores: the torch-CPU oracle port, fp32, all threads, bounded sample."""
+    from oracle import synchformer_oracle as O
+    from synchformer_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.synthetic_state_dict(1337, n_segments=S)
+    vis = synth.synthetic_video(n_clips, S, 0)
+    wave = synth.synthetic_waveform(n_clips, S, 0)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            aud = O.mel_frontend(wave).float().unsqueeze(2)
+            O.forward(sd, vis, aud)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_clips / sec, sec
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_clips = 1
+    value, sec = cpu_oracle_clips_per_sec(args.segments, n_clips, max(1, min(args.steps, 2)), min(args.warmup, 1))
+    sample = f'{n_clips} clip x {args.segments} segments per step, fp32, torch CPU oracle port of the reference forward (mel + encoders + sync)'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'clips/sec offset inference (5s-style clip: S x 0.64 s segments, 224p RGB + 16 kHz)', 'value': value,
+        'unit': 'clips/s', 'n_gpus': args.gpus, 'steps': max(1, min(args.steps, 2)), 'warmup': min(args.warmup, 1), 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'sync.yaml inference, batch={args.batch}, {args.segments} segments/clip (CPU sample: {n_clips} clip/step)'},
+        'cpu_baseline': {'value': value, 'unit': 'clips/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }), flush=True)
+
+
+class GemmTimer:
+    """CUDA-event timing of every GEMM launch inside the timed region, on the launching stream (roofline.achieved)."""
+
+    def __init__(self, ops):
+        self.ops, self.records, self.orig = ops, [], ops.gemm
+
+    def __enter__(self):
+        def timed(a, w, bias, out=None, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = self.orig(a, w, bias, out, **kw)
+            e.record()
+            self.records.append((2.0 * a.shape[0] * w.shape[0] * w.shape[1], s, e))
+            return r
+        self.ops.gemm = timed
+        import synchformer_b200.model as M
+        self._m = M
+        return self
+
+    def __exit__(self, *exc):
+        self.ops.gemm = self.orig
+
+    def summary(self):
+        flops = sum(f for f, _, _ in self.records)
+        ms = sum(s.elapsed_time(e) for _, s, e in self.records)
+        return flops, ms, len(self.records)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=64, help='clips per GPU per step')
+    ap.add_argument('--segments', type=int, default=8)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from synchformer_b200 import model as M, ops, parallel, synth
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl b200 needs a CUDA device (there is no CPU path)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    ops.device_check()
+
+    B, S = args.batch, args.segments                    # per-rank clips; global batch = B * world (weak scaling)
+    model = M.build_synchformer(n_segments=S, state_dict=synth.synthetic_state_dict(1337, n_segments=S), device=dev)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    # inputs resident in HBM: fp16 video as RGBToHalfToZeroOne delivers it (2.47 GB per rank at B=64,S=8 >> 126 MB L2), raw waveform
+    vis = (torch.rand(B, S, 16, 3, 224, 224, device=dev, generator=g) * 2 - 1).half()
+    t = torch.arange(S * 5120 + 5120, device=dev, dtype=torch.float32) / 16000.0
+    wave = torch.stack([torch.sin(2 * torch.pi * 440.0 * 2 ** (b / 12.0) * t).unfold(0, 10240, 5120)[:S] for b in range(B)]).contiguous()
+    # host copies for the end-to-end leg (pinned)
+    vis_h = vis.cpu().pin_memory()
+    wave_h = wave.cpu().pin_memory()
+
+    def step(v, w):
+        with torch.no_grad():
+            mel = ops.mel_frontend(w).unsqueeze(2)                      # (B, S, 1, 128, 66)
+            if world == 1:
+                return model(v, mel)[1]
+            # this rank's clips are its contiguous chunk of the global flattened segment list
+            return parallel.synchformer_forward_sharded(model, v.view(B * S, 16, 3, 224, 224), mel.view(B * S, 1, 128, 66), B * world, S)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        logits = step(vis, wave)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with GemmTimer(ops) as gt:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            logits = step(vis, wave)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ops.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    gemm_flops, gemm_ms, gemm_n = gt.summary()
+
+    # end-to-end: the public call (Synchformer.forward) fed from pinned HOST buffers, logits read back, inside the timed region
+    vis_d, wave_d = torch.empty_like(vis), torch.empty_like(wave)
+    del vis, wave
+
+    def e2e_step():
+        vis_d.copy_(vis_h, non_blocking=True)
+        wave_d.copy_(wave_h, non_blocking=True)
+        return step(vis_d, wave_d).float().cpu()
+    e2e_step()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        out_h = e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    tm = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tm[0]), float(tm[1])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        value = B * world * args.steps / (ms / 1e3)
+        e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        result = {
+            'metric': 'clips/sec offset inference (5s-style clip: S x 0.64 s segments, 224p RGB + 16 kHz)', 'value': value, 'unit': 'clips/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': f'sync.yaml inference, batch={B} clips/GPU, {S} segments/clip, bf16 GEMMs (fp32 accumulate, fp32 residual stream)',
+                       'global_batch': B * world, 'segments': S, 'parallelism': f'dp{world} (segment-sharded encoders + 1 all-gather)' if world > 1 else 'single GPU',
+                       'l2_policy': 'inputs larger than L2 (2.47 GB fp16 video per rank); activations stream through HBM',
+                       'weights': 'synthetic_state_dict(seed 1337), random-init-like, non-zero patch embedding'},
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
+                         'frac': (achieved / peaks['sustained']) if achieved else None, 'traffic': None,
+                         'kernel': 'gemm_bf16_tcgen05_kernel', 'launches_timed': gemm_n, 'gemm_ms_per_step': gemm_ms / args.steps,
+                         'peak_source': peaks['source'] + ', sustained bf16 (kernel timed inside a long step)',
+                         'step_frac_canonical': value * flops_per_clip(S) / world / (peaks['sustained'] * 1e12),
+                         'flops_per_clip_canonical': flops_per_clip(S)},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'clips/s', 'h2d_bytes_per_step': vis_h.numel() * vis_h.element_size() + wave_h.numel() * 4,
+                    'd2h_bytes_per_step': out_h.numel() * 4, 'steps': e2e_steps},
+            'gpu_launches': launches,
+            'logits_checksum': float(logits.float().abs().sum()),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cv, csec = cpu_oracle_clips_per_sec(S, 1, 1, 0)
+            result['cpu_baseline'] = {'value': cv, 'unit': 'clips/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                      'sample': f'1 clip x {S} segments, fp32 torch CPU oracle port of the reference forward, {csec:.1f} s'}
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

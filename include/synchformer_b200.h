@@ -1,0 +1,133 @@
+/*
+ * synchformer_b200 — C-ABI of the B200 (sm_100a) kernels behind `model.sync_model.Synchformer.forward`.
+ *
+ * The reference (v-iashin/Synchformer) is pure Python/PyTorch and has no FFI of its own: every entry point
+ * below replaces a group of torch ops on the hot path and cites the reference lines it stands in for
+ * (paths relative to the reference root).  The host side (`synchformer_b200/model.py`) mirrors the
+ * reference's `Synchformer` constructor / forward / state_dict surface and calls these through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise
+ *   - `bf16` buffers are passed as `void*` (raw __nv_bfloat16), fp32 as `float*`
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never allocates device
+ *     memory, never synchronises; the caller owns all buffers
+ *   - return value: 0 = ok, negative = SFB_E_* (no exceptions cross the ABI); `sfb_last_error()` gives text
+ *   - leading dimensions / strides are in ELEMENTS
+ */
+#ifndef SYNCHFORMER_B200_H
+#define SYNCHFORMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_OK 0
+#define SFB_E_INVALID (-1)   /* bad argument (shape / alignment / null pointer) */
+#define SFB_E_CUDA (-2)      /* a CUDA runtime / driver call failed */
+#define SFB_E_UNSUPPORTED (-3)
+
+/* library / device probing (host-only, no kernels) */
+int sfb_abi_version(void);
+const char *sfb_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), SFB_E_UNSUPPORTED otherwise */
+int sfb_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K5 — every nn.Linear on the path (vit_helper.py:105,156,393-396; modeling_ast.py:149-152,200,258,272;
+ * modules/transformer.py:62-64,74,87-92; motionformer.py:329 via nn.TransformerEncoderLayer; sync_model.py:55-56)
+ *
+ *   out[M,N] = epilogue( A[M,K] (bf16, row stride lda) x W[N,K]^T (bf16, row stride K) + bias[N] (fp32) )
+ *
+ * epilogue flags: SFB_GEMM_GELU      exact erf GELU (nn.GELU / HF GELUActivation)
+ *                 SFB_GEMM_RESIDUAL  += residual[M,N] fp32 (row stride ldr; ldr == 0 broadcasts one row)
+ *                 SFB_GEMM_OUT_F32   write fp32 instead of bf16 (out may alias residual)
+ * tcgen05.mma (128x256x16 UMMA, fp32 accumulators in TMEM), TMA-fed 4-stage smem ring, persistent CTAs.
+ * Requirements: K % 8 == 0, lda % 8 == 0, N % 8 == 0, ldo % 8 == 0, A/W 16-byte aligned.
+ * `impl`: 0 = tcgen05 (product path); 1 = plain CUDA-core kernel kept only as a bring-up cross-check. */
+#define SFB_GEMM_GELU 1
+#define SFB_GEMM_RESIDUAL 2
+#define SFB_GEMM_OUT_F32 4
+int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const float *bias, const float *residual, int64_t ldr,
+                  void *out, int64_t ldo, int M, int N, int K, int flags, int impl, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K4 — nn.LayerNorm over D = 768 with fp32 statistics (eps 1e-6 Motionformer/aggregators
+ * video_model_builder.py:39, motionformer.py:126; 1e-12 AST modeling_ast.py:291-292,464; 1e-5 sync
+ * transformer.py:84-85, sync_model.py:126-127,143).
+ * Output row r reads input row  (r / group) * group_stride + offset + (r % group)   (drops CLS / aux tokens
+ * without a copy: motionformer.py:229-232, ast.py:232-233).  If gamma2 != NULL a second LayerNorm
+ * (gamma2, beta2, eps2) is applied to the result of the first in registers (final encoder norm followed by the
+ * aggregator's norm1, motionformer.py:231 + nn.TransformerEncoderLayer norm_first). */
+int sfb_layernorm(const float *x, int64_t ldx, void *out, int64_t ldo, int out_f32, const float *gamma, const float *beta,
+                  float eps, const float *gamma2, const float *beta2, float eps2, int rows, int group, int group_stride,
+                  int offset, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K6-K11 — multi-head softmax attention on strided bf16 Q/K/V views (no rearrange/cat copies).
+ * A "problem" is (outer o, inner i, head h); its rows live at
+ *     q   + o*q_outer  + i*q_inner  + h*head_dim + r*q_row          r in [0, Lq)
+ *     k/v + o*kv_outer + i*kv_inner + h*head_dim + r*kv_row         r in [0, Lk)
+ *     out + o*o_outer  + i*o_inner  + h*head_dim + r*o_row
+ * and, if k_prefix != NULL, one extra key/value row (the CLS token, vit_helper.py:129-134; the aggregator CLS,
+ * motionformer.py:305-306) at  k_prefix/v_prefix + o*prefix_outer + h*head_dim  is placed BEFORE the Lk rows.
+ * softmax(scale * q k^T) v with fp32 scores/statistics.
+ * Covers: time attention (8 x 9, vit_helper.py:100-158 '(b n) f d'), space attention (196 x 197, '(b f) n d'),
+ * Motionformer CLS query (1 x 1569, vit_helper.py:124), AST MHSA (74 x 74, modeling_ast.py:145-184),
+ * CLS-aggregator attention rows (1 x 197 / 1 x 13, motionformer.py:329), sync MHSA (198 x 198, hd 96,
+ * modules/transformer.py:58-76).  head_dim in {64, 96}. */
+typedef struct sfb_attn_desc {
+    const void *q, *k, *v;
+    const void *k_prefix, *v_prefix; /* NULL = no prefix row */
+    void *out;
+    int64_t q_outer, q_inner, q_row;
+    int64_t kv_outer, kv_inner, kv_row;
+    int64_t o_outer, o_inner, o_row;
+    int64_t prefix_outer;
+    int32_t n_outer, n_inner, n_heads, head_dim, Lq, Lk;
+    float scale;
+    int32_t impl; /* 0 = auto (specialised kernels), 1 = generic CUDA-core kernel (bring-up cross-check) */
+} sfb_attn_desc;
+int sfb_attention(const sfb_attn_desc *desc, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K2 — PatchEmbed3D as im2col + GEMM (vit_helper.py:436-445).  vis is (n_seg, 16, 3, 224, 224) in the layout
+ * Synchformer.forward receives it (sync_model.py:38-46; the permute at :74 is only a view).
+ * in_dtype: 0 fp32, 1 fp16, 2 bf16, 3 uint8 (uint8 fuses RGBToHalfToZeroOne + RGBNormalize(.5,.5),
+ * dataset/transforms.py:647-669).  A is (n_seg*1568, 1536) bf16, K order (c, dt, dy, dx) = Conv3d weight order. */
+int sfb_im2col_video(const void *vis, int in_dtype, void *A, int n_seg, void *stream);
+/* + bias already added by the GEMM; adds pos_embed[1+n] + temp_embed[f], prepends cls_token + pos_embed[0]
+ * (video_model_builder.py:221-254).  patch (n_seg*1568, 768) fp32 -> x (n_seg, 1569, 768) fp32 */
+int sfb_video_tokens(const float *patch, const float *cls_token, const float *pos_embed, const float *temp_embed, float *x,
+                     int n_seg, void *stream);
+
+/* K3 — ASTPatchEmbeddings + ASTEmbeddings (modeling_ast.py:113-117, 83-93).  spec (n_seg, 128, 66) fp32
+ * [freq, time]; A (n_seg*72, 256) bf16; tokens 2 + f*6 + t. */
+int sfb_im2col_ast(const float *spec, void *A, int n_seg, void *stream);
+int sfb_ast_tokens(const float *patch, const float *cls_token, const float *dist_token, const float *pos_embed, float *x,
+                   int n_seg, void *stream);
+
+/* K12 — GlobalTransformer token assembly (sync_model.py:150-167, modules/transformer.py:129-130):
+ * x[b] = [OFF, LN_vis(v[b, 0..8S)), MOD, LN_aud(a[b, 0..6S))] + pos_emb;  v (B, 8S, 768), a (B, 6S, 768) fp32 */
+int sfb_sync_tokens(const float *v, const float *a, const float *vis_ln_w, const float *vis_ln_b, const float *aud_ln_w,
+                    const float *aud_ln_b, float eps, const float *off_tok, const float *mod_tok, const float *pos_emb, float *x,
+                    int B, int S, void *stream);
+/* K13 — ln_f on token 0 + Linear(768 -> n_cls) in fp32 (sync_model.py:169-172).  x (B, T, 768) fp32 */
+int sfb_sync_head(const float *x, int T, const float *ln_w, const float *ln_b, float eps, const float *W, const float *b,
+                  float *logits, int B, int n_cls, void *stream);
+
+/* fp32 -> bf16 cast of n elements (n % 4 == 0); used for weights at load time and the aggregator features */
+int sfb_cast_f32_bf16(const float *in, void *out, int64_t n, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K1 — mel front-end (dataset/transforms.py:815-871 = torchaudio MelSpectrogram(n_fft 1024, win 400, hop 160,
+ * 128 mels, power 2) -> log(x + 1e-6) -> pad T 65->66 with 0.0 -> (x + 4.2677393) / (2 * 4.5689974)).
+ * wave (n_seg, 10240) fp32 -> out (n_seg, 128, 66) fp32.  The first call uploads three constant tables
+ * (twiddles, window, filterbank) to static device arrays with a synchronous copy. */
+int sfb_mel_frontend(const float *wave, float *out, int n_seg, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNCHFORMER_B200_H */

@@ -57,8 +57,8 @@ def _softmax_av(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
     return torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v
 
 
-def _cast_sd(sd: Dict[str, Tensor], dtype) -> Dict[str, Tensor]:
-    return {k: v.detach().to('cpu', dtype) for k, v in sd.items()}
+def _cast_sd(sd: Dict[str, Tensor], dtype, device='cpu') -> Dict[str, Tensor]:
+    return {k: v.detach().to(device, dtype) for k, v in sd.items()}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -193,12 +193,12 @@ def cls_aggregator(sd, prefix: str, x: Tensor) -> Tensor:
     return (x + y)[:, 0]
 
 
-def extract_vfeats(sd, vis: Tensor, dtype=torch.float32, taps: Optional[dict] = None) -> Tensor:
+def extract_vfeats(sd, vis: Tensor, dtype=torch.float32, taps: Optional[dict] = None, device='cpu') -> Tensor:
     """Synchformer.extract_vfeats (sync_model.py:72-80) -> MotionFormer.forward/forward_segments
     (motionformer.py:182-252).  vis (B, S, 16, 3, 224, 224) -> (B, S, 8, 768)."""
-    sd = _cast_sd({k: v for k, v in sd.items() if k.startswith('vfeat_extractor.')}, dtype)
+    sd = _cast_sd({k: v for k, v in sd.items() if k.startswith('vfeat_extractor.')}, dtype, device)
     B, S = vis.shape[:2]
-    x = video_patch_embed(sd, vis.reshape(B * S, *vis.shape[2:]).to('cpu', dtype))
+    x = video_patch_embed(sd, vis.reshape(B * S, *vis.shape[2:]).to(device, dtype))
     if taps is not None:
         taps['v_embed'] = x
     for i in range(V_DEPTH):
@@ -243,12 +243,12 @@ def ast_layer(sd, i: int, x: Tensor) -> Tensor:
     return x + _lin(y, sd[p + 'output.dense.weight'], sd[p + 'output.dense.bias'])
 
 
-def extract_afeats(sd, aud: Tensor, dtype=torch.float32, taps: Optional[dict] = None) -> Tensor:
+def extract_afeats(sd, aud: Tensor, dtype=torch.float32, taps: Optional[dict] = None, device='cpu') -> Tensor:
     """Synchformer.extract_afeats (sync_model.py:82-89) -> AST.forward/forward_segments (ast.py:137-201).
     aud (B, S, 1, 128, 66) -> (B, S, 6, 768).  The two transposes (sync_model.py:84, modeling_ast.py:115) cancel."""
-    sd = _cast_sd({k: v for k, v in sd.items() if k.startswith('afeat_extractor.')}, dtype)
+    sd = _cast_sd({k: v for k, v in sd.items() if k.startswith('afeat_extractor.')}, dtype, device)
     B, S = aud.shape[:2]
-    x = audio_patch_embed(sd, aud.reshape(B * S, 128, 66).to('cpu', dtype))
+    x = audio_patch_embed(sd, aud.reshape(B * S, 128, 66).to(device, dtype))
     if taps is not None:
         taps['a_embed'] = x
     for i in range(A_DEPTH):
@@ -281,14 +281,14 @@ def sync_block(sd, i: int, x: Tensor) -> Tensor:
     return x + _lin(y, sd[p + 'mlp.2.weight'], sd[p + 'mlp.2.bias'])
 
 
-def sync_head(sd, vfeat: Tensor, afeat: Tensor, dtype=torch.float32, head: str = 'off_head') -> Tensor:
+def sync_head(sd, vfeat: Tensor, afeat: Tensor, dtype=torch.float32, head: str = 'off_head', device='cpu') -> Tensor:
     """sync_model.py:55-62 (vproj/aproj, flatten segments) + GlobalTransformer.forward :150-173.
     vfeat (B,S,8,768), afeat (B,S,6,768) -> logits (B, 21).  head='sync_head' gives the 2-class variant
     (GlobalTransformerWithSyncabilityHead :176-190)."""
-    sd = _cast_sd({k: v for k, v in sd.items() if k.split('.')[0] in ('vproj', 'aproj', 'transformer')}, dtype)
+    sd = _cast_sd({k: v for k, v in sd.items() if k.split('.')[0] in ('vproj', 'aproj', 'transformer')}, dtype, device)
     B, S = vfeat.shape[:2]
-    v = _lin(vfeat.to('cpu', dtype), sd['vproj.weight'], sd['vproj.bias']).reshape(B, S * 8, D)
-    a = _lin(afeat.to('cpu', dtype), sd['aproj.weight'], sd['aproj.bias']).reshape(B, S * 6, D)
+    v = _lin(vfeat.to(device, dtype), sd['vproj.weight'], sd['vproj.bias']).reshape(B, S * 8, D)
+    a = _lin(afeat.to(device, dtype), sd['aproj.weight'], sd['aproj.bias']).reshape(B, S * 6, D)
     t = 'transformer.'
     v = _ln(v, sd[t + 'vis_in_lnorm.weight'], sd[t + 'vis_in_lnorm.bias'], EPS_S)
     a = _ln(a, sd[t + 'aud_in_lnorm.weight'], sd[t + 'aud_in_lnorm.bias'], EPS_S)
@@ -302,16 +302,17 @@ def sync_head(sd, vfeat: Tensor, afeat: Tensor, dtype=torch.float32, head: str =
     return _lin(x[:, 0], sd[t + head + '.weight'], sd[t + head + '.bias'])
 
 
-def forward(sd, vis: Tensor, aud: Tensor, targets: Optional[Tensor] = None, dtype=torch.float32, taps: Optional[dict] = None):
-    """Synchformer.forward sync_model.py:38-70 -> (loss | None, logits (B, 21))."""
-    vf = extract_vfeats(sd, vis, dtype, taps)
-    af = extract_afeats(sd, aud, dtype, taps)
+def forward(sd, vis: Tensor, aud: Tensor, targets: Optional[Tensor] = None, dtype=torch.float32, taps: Optional[dict] = None, device='cpu'):
+    """Synchformer.forward sync_model.py:38-70 -> (loss | None, logits (B, 21)).  `device` exists so that tests can run the same
+    restatement with torch's CUDA library kernels as a second opinion; the oracle proper is the CPU run."""
+    vf = extract_vfeats(sd, vis, dtype, taps, device)
+    af = extract_afeats(sd, aud, dtype, taps, device)
     if taps is not None:
         taps['vfeats'], taps['afeats'] = vf, af
-    logits = sync_head(sd, vf, af, dtype)
+    logits = sync_head(sd, vf, af, dtype, device=device)
     loss = None
     if targets is not None:                                   # compute_loss sync_model.py:91-99
-        loss = F.cross_entropy(logits.float(), targets.to('cpu'))
+        loss = F.cross_entropy(logits.float(), targets.to(device))
     return loss, logits
 
 

@@ -1,0 +1,430 @@
+// K6-K11: softmax attention on strided bf16 Q/K/V views of the fused qkv activations (see sfb_attn_desc).
+//
+// Three kernels behind one entry point:
+//   attn_mma_kernel<HD>    Lq >= 16: one CTA per (outer, inner, head).  Q/K/V rows are staged once in padded shared
+//                          memory with cp.async, each warp owns 16 query rows and walks the keys in chunks of 64 with
+//                          mma.sync.m16n8k16 (bf16 in, fp32 accumulate) for QK^T and PV and a register-resident online
+//                          softmax (quad shuffles only).  Space attention 196x197, AST 74x74, sync 198x198 (hd 96).
+//   attn_time_kernel       Lq = Lk = 8 + CLS prefix, hd 64 (Motionformer time attention): one thread per (query frame,
+//                          head); the 8 lanes that share a (position, head) read the same K/V addresses, so the loads
+//                          broadcast and no shared memory or shuffles are needed.
+//   attn_generic_kernel<HD> one warp per query row, lanes split the head dim.  Used for single-query rows (Motionformer
+//                          CLS 1x1569, aggregator CLS 1x197 / 1x13) and as the bring-up cross-check for the other two.
+// All keep scores and statistics in fp32; nothing is materialised in HBM (the reference materialises the attention
+// matrix and ~20 rearrange/cat copies per block: vit_helper.py:34-42,106-153; modeling_ast.py:156-176;
+// modules/transformer.py:67-70).
+#include "common.cuh"
+
+namespace sfb {
+namespace attn {
+
+struct Desc {
+    const __nv_bfloat16 *q, *k, *v, *kp, *vp;
+    __nv_bfloat16 *out;
+    int64_t q_outer, q_inner, q_row;
+    int64_t kv_outer, kv_inner, kv_row;
+    int64_t o_outer, o_inner, o_row;
+    int64_t prefix_outer;
+    int has_prefix;
+    int n_outer, n_inner, n_heads, Lq, Lk;
+    float scale;
+};
+
+// ------------------------------------------------------------------------------------------- generic kernel
+template <int HD>
+__global__ void __launch_bounds__(256) attn_generic_kernel(const Desc d) {
+    constexpr int E = HD / 32;  // elements per lane
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const int64_t total = static_cast<int64_t>(d.n_outer) * d.n_inner * d.n_heads * d.Lq;
+    if (wid >= total) return;
+    const int r = static_cast<int>(wid % d.Lq);
+    int64_t t = wid / d.Lq;
+    const int h = static_cast<int>(t % d.n_heads);
+    t /= d.n_heads;
+    const int i = static_cast<int>(t % d.n_inner);
+    const int o = static_cast<int>(t / d.n_inner);
+
+    const __nv_bfloat16 *qp = d.q + o * d.q_outer + i * d.q_inner + static_cast<int64_t>(r) * d.q_row + h * HD + lane * E;
+    const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD + lane * E;
+    const int64_t pre_base = o * d.prefix_outer + h * HD + lane * E;
+    float q[E], acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) q[e] = __bfloat162float(qp[e]) * d.scale, acc[e] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    const int Lkp = d.Lk + d.has_prefix;
+    for (int j0 = 0; j0 < Lkp; j0 += 4) {
+        float kk[4][E], vv[4][E], s[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u;
+            if (j < Lkp) {
+                const bool pre = d.has_prefix && j == 0;
+                const int64_t off = pre ? pre_base : kv_base + static_cast<int64_t>(j - d.has_prefix) * d.kv_row;
+                const __nv_bfloat16 *kr = (pre ? d.kp : d.k) + off, *vr = (pre ? d.vp : d.v) + off;
+#pragma unroll
+                for (int e = 0; e < E; ++e) kk[u][e] = __bfloat162float(kr[e]), vv[u][e] = __bfloat162float(vr[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) kk[u][e] = 0.f, vv[u][e] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float p = 0.f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) p = fmaf(q[e], kk[u][e], p);
+            s[u] = (j0 + u < Lkp) ? warp_sum(p) : -INFINITY;
+        }
+        const float m_new = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), m);
+        const float corr = __expf(m - m_new);
+        l *= corr;
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] *= corr;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float p = __expf(s[u] - m_new);
+            l += p;
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = fmaf(p, vv[u][e], acc[e]);
+        }
+        m = m_new;
+    }
+    __nv_bfloat16 *op = d.out + o * d.o_outer + i * d.o_inner + static_cast<int64_t>(r) * d.o_row + h * HD + lane * E;
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int e = 0; e < E; ++e) op[e] = __float2bfloat16_rn(acc[e] * inv);
+}
+
+// ------------------------------------------------------------------------------ Motionformer time attention
+// lane = frame (0..7) + 8 * (head within a group of 4); a warp covers one (segment, position, head-group).
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float *f) {
+    f[0] = __uint_as_float(u.x << 16), f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16), f[3] = __uint_as_float(u.y & 0xffff0000u);
+    f[4] = __uint_as_float(u.z << 16), f[5] = __uint_as_float(u.z & 0xffff0000u);
+    f[6] = __uint_as_float(u.w << 16), f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+__global__ void __launch_bounds__(256) attn_time_kernel(const Desc d) {
+    constexpr int HD = 64, L = 8;
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const int hg_per = d.n_heads / 4;
+    const int64_t total = static_cast<int64_t>(d.n_outer) * d.n_inner * hg_per;
+    if (wid >= total) return;
+    const int hg = static_cast<int>(wid % hg_per);
+    const int64_t t = wid / hg_per;
+    const int i = static_cast<int>(t % d.n_inner);
+    const int o = static_cast<int>(t / d.n_inner);
+    const int f = lane & 7;
+    const int h = hg * 4 + (lane >> 3);
+
+    const uint4 *qp = reinterpret_cast<const uint4 *>(d.q + o * d.q_outer + i * d.q_inner + static_cast<int64_t>(f) * d.q_row + h * HD);
+    float q[HD];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bf16x8_to_f32(__ldg(qp + c), q + 8 * c);
+    const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD;
+    const int64_t pre_base = o * d.prefix_outer + h * HD;
+
+    float s[L + 1];
+#pragma unroll
+    for (int j = 0; j < L + 1; ++j) {
+        const uint4 *kp = reinterpret_cast<const uint4 *>(j == 0 ? d.kp + pre_base : d.k + kv_base + static_cast<int64_t>(j - 1) * d.kv_row);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float kf[8];
+            bf16x8_to_f32(__ldg(kp + c), kf);
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) a0 = fmaf(q[8 * c + e], kf[e], a0), a1 = fmaf(q[8 * c + e + 1], kf[e + 1], a1);
+        }
+        s[j] = (a0 + a1) * d.scale;
+    }
+    float m = s[0];
+#pragma unroll
+    for (int j = 1; j < L + 1; ++j) m = fmaxf(m, s[j]);
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < L + 1; ++j) s[j] = __expf(s[j] - m), l += s[j];
+    const float inv = 1.0f / l;
+    // reuse q[] as the output accumulator
+#pragma unroll
+    for (int e = 0; e < HD; ++e) q[e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < L + 1; ++j) {
+        const uint4 *vp = reinterpret_cast<const uint4 *>(j == 0 ? d.vp + pre_base : d.v + kv_base + static_cast<int64_t>(j - 1) * d.kv_row);
+        const float p = s[j] * inv;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float vf[8];
+            bf16x8_to_f32(__ldg(vp + c), vf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) q[8 * c + e] = fmaf(p, vf[e], q[8 * c + e]);
+        }
+    }
+    uint4 *op = reinterpret_cast<uint4 *>(d.out + o * d.o_outer + i * d.o_inner + static_cast<int64_t>(f) * d.o_row + h * HD);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(q[8 * c], q[8 * c + 1]);
+        u.y = pack_bf16x2(q[8 * c + 2], q[8 * c + 3]);
+        u.z = pack_bf16x2(q[8 * c + 4], q[8 * c + 5]);
+        u.w = pack_bf16x2(q[8 * c + 6], q[8 * c + 7]);
+        op[c] = u;
+    }
+}
+
+// ------------------------------------------------------------------------------------- tensor-core kernel
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(HD == 64 ? 512 : 416) attn_mma_kernel(const Desc d, int Lq_pad, int Lk_pad) {
+    constexpr int PITCH = HD * 2 + 16;      // bytes per smem row; +16 keeps ldmatrix rows on distinct bank groups
+    constexpr int CHUNKS = HD / 8;          // 16-byte chunks per row
+    constexpr int KSTEPS = HD / 16;         // k16 steps over the head dim
+    constexpr int NT_O = HD / 8;            // n8 tiles of the output
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const uint32_t sK = sQ + Lq_pad * PITCH;
+    const uint32_t sV = sK + Lk_pad * PITCH;
+
+    int pidx = blockIdx.x;
+    const int h = pidx % d.n_heads;
+    pidx /= d.n_heads;
+    const int i = pidx % d.n_inner;
+    const int o = pidx / d.n_inner;
+    const int Lkp = d.Lk + d.has_prefix;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    // ---- stage Q, K, V (zero-fill the padding rows so 0 * garbage never produces NaN) ----
+    const __nv_bfloat16 *qg = d.q + o * d.q_outer + i * d.q_inner + h * HD;
+    for (int c = tid; c < Lq_pad * CHUNKS; c += nthr) {
+        const int r = c / CHUNKS, cc = c % CHUNKS;
+        const uint32_t dst = sQ + r * PITCH + cc * 16;
+        if (r < d.Lq)
+            cp_async16(dst, qg + static_cast<int64_t>(r) * d.q_row + cc * 8);
+        else
+            *reinterpret_cast<uint4 *>(smem + (dst - sQ)) = make_uint4(0, 0, 0, 0);
+    }
+    const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD;
+    const int64_t pre_base = o * d.prefix_outer + h * HD;
+    for (int c = tid; c < Lk_pad * CHUNKS; c += nthr) {
+        const int r = c / CHUNKS, cc = c % CHUNKS;
+        const uint32_t dk = sK + r * PITCH + cc * 16, dv = sV + r * PITCH + cc * 16;
+        if (r < Lkp) {
+            const bool pre = d.has_prefix && r == 0;
+            const int64_t off = (pre ? pre_base : kv_base + static_cast<int64_t>(r - d.has_prefix) * d.kv_row) + cc * 8;
+            cp_async16(dk, (pre ? d.kp : d.k) + off);
+            cp_async16(dv, (pre ? d.vp : d.v) + off);
+        } else {
+            *reinterpret_cast<uint4 *>(smem + (dk - sQ)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(smem + (dv - sQ)) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int q0 = warp * 16;
+    if (q0 >= Lq_pad) return;
+
+    // Q fragments for this warp's 16 rows (A operand, row-major): lanes 0-15 -> rows, lanes 16-31 -> +8 columns
+    uint32_t qa[KSTEPS][4];
+    {
+        const uint32_t base = sQ + (q0 + (lane & 15)) * PITCH + (lane >> 4) * 16;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) ldmatrix_x4(base + ks * 32, qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    }
+    float oacc[NT_O][4];
+#pragma unroll
+    for (int n = 0; n < NT_O; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g+8
+    const float sl2 = d.scale * 1.4426950408889634f;            // scores are kept in log2 units
+
+    for (int kc = 0; kc < Lk_pad; kc += 64) {
+        const int nkb = min(4, (Lk_pad - kc) >> 4);   // 16-key blocks in this chunk (warp-uniform)
+        float s[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+        // ---- S = Q K^T : per 16-key block two n8 tiles; B fragments straight from the row-major K rows ----
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            if (kb < nkb) {
+                const uint32_t kaddr = sK + (kc + kb * 16 + (lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 16;
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4(kaddr + ks * 32, b0, b1, b2, b3);
+                    mma_bf16_16816(s[2 * kb], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+                    mma_bf16_16816(s[2 * kb + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+                }
+            }
+        }
+        // ---- scale, mask the padded keys, online softmax ----
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const int key = kc + n * 8 + t4 * 2;
+            const bool live = n < 2 * nkb;
+            s[n][0] = (live && key < Lkp) ? s[n][0] * sl2 : -INFINITY;
+            s[n][1] = (live && key + 1 < Lkp) ? s[n][1] * sl2 : -INFINITY;
+            s[n][2] = (live && key < Lkp) ? s[n][2] * sl2 : -INFINITY;
+            s[n][3] = (live && key + 1 < Lkp) ? s[n][3] * sl2 : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float c0 = fast_exp2(m0 - mx0), c1 = fast_exp2(m1 - mx1);   // first chunk: exp2(-inf) = 0
+        m0 = mx0, m1 = mx1;
+        float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            s[n][0] = fast_exp2(s[n][0] - mx0), s[n][1] = fast_exp2(s[n][1] - mx0);
+            s[n][2] = fast_exp2(s[n][2] - mx1), s[n][3] = fast_exp2(s[n][3] - mx1);
+            ps0 += s[n][0] + s[n][1];
+            ps1 += s[n][2] + s[n][3];
+        }
+        l0 = l0 * c0 + ps0;   // per-thread partial sums; reduced over the quad at the end
+        l1 = l1 * c1 + ps1;
+#pragma unroll
+        for (int n = 0; n < NT_O; ++n) oacc[n][0] *= c0, oacc[n][1] *= c0, oacc[n][2] *= c1, oacc[n][3] *= c1;
+        // ---- O += P V : P from the S accumulators (C layout == A layout), V^T fragments via ldmatrix.trans ----
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            if (kb < nkb) {
+                const uint32_t a0 = pack_bf16x2(s[2 * kb][0], s[2 * kb][1]);
+                const uint32_t a1 = pack_bf16x2(s[2 * kb][2], s[2 * kb][3]);
+                const uint32_t a2 = pack_bf16x2(s[2 * kb + 1][0], s[2 * kb + 1][1]);
+                const uint32_t a3 = pack_bf16x2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
+                const uint32_t vaddr = sV + (kc + kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16;
+#pragma unroll
+                for (int n2 = 0; n2 < NT_O / 2; ++n2) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4_trans(vaddr + n2 * 32, b0, b1, b2, b3);
+                    mma_bf16_16816(oacc[2 * n2], a0, a1, a2, a3, b0, b1);
+                    mma_bf16_16816(oacc[2 * n2 + 1], a0, a1, a2, a3, b2, b3);
+                }
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+
+    // ---- stage the 16 x HD output tile in this warp's (now dead) Q rows, then store 16 B per lane ----
+    __syncwarp();
+    uint8_t *so = smem + q0 * PITCH;
+#pragma unroll
+    for (int n = 0; n < NT_O; ++n) {
+        *reinterpret_cast<uint32_t *>(so + g * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][0] * i0, oacc[n][1] * i0);
+        *reinterpret_cast<uint32_t *>(so + (g + 8) * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][2] * i1, oacc[n][3] * i1);
+    }
+    __syncwarp();
+    __nv_bfloat16 *og = d.out + o * d.o_outer + i * d.o_inner + h * HD;
+    for (int c = lane; c < 16 * CHUNKS; c += 32) {
+        const int r = c / CHUNKS, cc = c % CHUNKS;
+        if (q0 + r < d.Lq)
+            *reinterpret_cast<uint4 *>(og + static_cast<int64_t>(q0 + r) * d.o_row + cc * 8) = *reinterpret_cast<const uint4 *>(so + r * PITCH + cc * 16);
+    }
+}
+
+}  // namespace attn
+}  // namespace sfb
+
+extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
+    using namespace sfb;
+    using namespace sfb::attn;
+    SFB_CHECK_ARG(desc != nullptr, "sfb_attention: null descriptor");
+    SFB_CHECK_ARG(desc->q && desc->k && desc->v && desc->out, "sfb_attention: null pointer");
+    SFB_CHECK_ARG(desc->head_dim == 64 || desc->head_dim == 96, "sfb_attention: head_dim %d not in {64, 96}", desc->head_dim);
+    SFB_CHECK_ARG(desc->n_outer > 0 && desc->n_inner > 0 && desc->n_heads > 0 && desc->Lq > 0 && desc->Lk > 0, "sfb_attention: bad sizes");
+    Desc d;
+    d.q = reinterpret_cast<const __nv_bfloat16 *>(desc->q);
+    d.k = reinterpret_cast<const __nv_bfloat16 *>(desc->k);
+    d.v = reinterpret_cast<const __nv_bfloat16 *>(desc->v);
+    d.out = reinterpret_cast<__nv_bfloat16 *>(desc->out);
+    d.q_outer = desc->q_outer, d.q_inner = desc->q_inner, d.q_row = desc->q_row;
+    d.kv_outer = desc->kv_outer, d.kv_inner = desc->kv_inner, d.kv_row = desc->kv_row;
+    d.o_outer = desc->o_outer, d.o_inner = desc->o_inner, d.o_row = desc->o_row;
+    SFB_CHECK_ARG((desc->k_prefix == nullptr) == (desc->v_prefix == nullptr), "sfb_attention: k_prefix / v_prefix must be given together");
+    d.kp = reinterpret_cast<const __nv_bfloat16 *>(desc->k_prefix);
+    d.vp = reinterpret_cast<const __nv_bfloat16 *>(desc->v_prefix);
+    d.prefix_outer = desc->prefix_outer, d.has_prefix = desc->k_prefix != nullptr ? 1 : 0;
+    d.n_outer = desc->n_outer, d.n_inner = desc->n_inner, d.n_heads = desc->n_heads, d.Lq = desc->Lq, d.Lk = desc->Lk;
+    d.scale = desc->scale;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int HD = desc->head_dim;
+
+    // vectorised kernels need 16-byte aligned rows
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(d.q) | reinterpret_cast<uintptr_t>(d.k) | reinterpret_cast<uintptr_t>(d.v) |
+                             reinterpret_cast<uintptr_t>(d.out) | reinterpret_cast<uintptr_t>(d.kp) | reinterpret_cast<uintptr_t>(d.vp)) & 15) == 0 &&
+                           ((d.q_outer | d.q_inner | d.q_row | d.kv_outer | d.kv_inner | d.kv_row | d.o_outer | d.o_inner | d.o_row |
+                             d.prefix_outer) % 8) == 0;
+    const int Lkp = d.Lk + d.has_prefix;
+    const int Lq_pad = (d.Lq + 15) & ~15, Lk_pad = (Lkp + 15) & ~15;
+    const int64_t mma_smem = static_cast<int64_t>(Lq_pad + 2 * Lk_pad) * (HD * 2 + 16);
+    const int64_t n_prob = static_cast<int64_t>(d.n_outer) * d.n_inner * d.n_heads;
+
+    if (desc->impl == 0 && aligned16 && d.Lq >= 16 && Lq_pad <= (HD == 64 ? 256 : 208) && mma_smem <= 200 * 1024) {
+        const int threads = (Lq_pad / 16) * 32;
+        SFB_CHECK_ARG(n_prob < (1ll << 31), "sfb_attention: too many problems");
+        if (HD == 64) {
+            static int64_t cur = 0;
+            if (mma_smem > cur) {
+                SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(mma_smem)));
+                cur = mma_smem;
+            }
+            attn_mma_kernel<64><<<static_cast<unsigned>(n_prob), threads, mma_smem, st>>>(d, Lq_pad, Lk_pad);
+        } else {
+            static int64_t cur = 0;
+            if (mma_smem > cur) {
+                SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(mma_smem)));
+                cur = mma_smem;
+            }
+            attn_mma_kernel<96><<<static_cast<unsigned>(n_prob), threads, mma_smem, st>>>(d, Lq_pad, Lk_pad);
+        }
+        SFB_CHECK_LAUNCH();
+        return SFB_OK;
+    }
+    if (desc->impl == 0 && aligned16 && HD == 64 && d.Lq == 8 && d.Lk == 8 && d.has_prefix && d.n_heads % 4 == 0) {
+        const int64_t warps = static_cast<int64_t>(d.n_outer) * d.n_inner * (d.n_heads / 4);
+        attn_time_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>(d);
+        SFB_CHECK_LAUNCH();
+        return SFB_OK;
+    }
+    const int64_t warps = n_prob * d.Lq;
+    SFB_CHECK_ARG((warps + 7) / 8 < (1ll << 31), "sfb_attention: too many rows");
+    if (HD == 64)
+        attn_generic_kernel<64><<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>(d);
+    else
+        attn_generic_kernel<96><<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>(d);
+    SFB_CHECK_LAUNCH();
+    return SFB_OK;
+}

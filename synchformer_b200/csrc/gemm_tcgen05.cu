@@ -1,0 +1,463 @@
+// K5: bf16 GEMM with fused bias / exact-GELU / fp32-residual epilogue for every nn.Linear on the path.
+//
+//   out[M,N] = epi( A[M,K] * W[N,K]^T + bias )          A, W bf16 K-major; fp32 accumulation
+//
+// sm_100a design (one persistent CTA per SM, 320 threads, warp-specialised):
+//   warp 0      TMA producer   cp.async.bulk.tensor 2D loads of a 128x64 A box and a 256x64 W box (128B swizzle)
+//                              into a 4-stage shared-memory ring, completion on "full" mbarriers
+//   warp 1      MMA issuer     one thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16) per stage,
+//                              accumulating in TMEM; tcgen05.commit releases the stage ("empty") and, after the
+//                              last k-block, publishes the accumulator ("tmem_full")
+//   warps 2-9   epilogue       tcgen05.ld 32x32b.x32 (TMEM -> registers), bias / GELU / residual, vectorised stores;
+//                              the 512 TMEM columns hold TWO 128x256 fp32 accumulators so the epilogue of tile i
+//                              overlaps the main loop of tile i+1
+// Tiles are walked n-fastest so the CTAs that share an A row-block run at the same time and hit it in L2;
+// W (<= 4.7 MB) is L2-resident throughout.  M / N / K tails are handled by TMA zero fill + epilogue masking.
+//
+// Reference ops replaced: nn.Linear at vit_helper.py:105,156,393-396; modeling_ast.py:149-152,200,258,272;
+// modules/transformer.py:62-64,74,87-92; nn.TransformerEncoderLayer linears (motionformer.py:329); sync_model.py:55-56.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sfb {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 1024;  // + slack for 1024-byte alignment
+constexpr uint32_t TMEM_COLS = 512;
+
+struct EpiParams {
+    const float *bias;
+    const float *residual;
+    int64_t ldr;
+    void *out;
+    int64_t ldo;
+    int M, N, K;
+    int flags;
+    int num_m_blocks, num_n_blocks;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (error at the next sync) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    #pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, one 64-element (128 B) atom along K:
+// start address >> 4 in [0,14), LBO unused (0), SBO = 8 rows * 128 B = 1024 B in [32,46), version 1 in [46,48),
+// layout type SWIZZLE_128B (= 2) in [61,64).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1024u >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// UMMA instruction descriptor for kind::f16: D fp32 (bit 4), A bf16 (bits 7-9 = 1), B bf16 (bits 10-12 = 1),
+// A and B K-major (bits 15, 16 = 0), N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const EpiParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 2 * kAccStages];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + kAccStages + a); };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < kAccStages; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), kEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {  // one full warp allocates all 512 TMEM columns (1 CTA per SM) and later frees them
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / p.num_n_blocks) * BLOCK_M;
+                const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = tiles_base + stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+                    tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m0);
+                    tma_load_2d(sa + A_BYTES, &tmap_w, full_bar(stage), kb * BLOCK_K, n0);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = tiles_base + stage * STAGE_BYTES;
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        umma_bf16(tmem_d, make_sw128_desc(sa + k * UMMA_K * 2), make_sw128_desc(sb + k * UMMA_K * 2), idesc,
+                                  static_cast<uint32_t>((kb | k) != 0));
+                    }
+                    umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete
+                if (++acc == kAccStages) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const int q = warp & 3;               // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
+        const int half = (warp - 2) >> 2;     // which 128 of the 256 accumulator columns
+        const bool gelu = (p.flags & SFB_GEMM_GELU) != 0;
+        const bool has_res = (p.flags & SFB_GEMM_RESIDUAL) != 0;
+        const bool out_f32 = (p.flags & SFB_GEMM_OUT_F32) != 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / p.num_n_blocks) * BLOCK_M;
+            const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
+            const int row = m0 + q * 32 + lane;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = n0 + half * 128 + c * 32;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + half * 128 + c * 32), r);
+                tmem_ld_wait();
+                if (row < p.M && col0 < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j < p.N) {
+                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+                                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+                            }
+                        }
+                    }
+                    if (gelu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    if (has_res) {
+                        const float *rp = p.residual + static_cast<int64_t>(row) * p.ldr + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j < p.N) {
+                                const float4 b = *reinterpret_cast<const float4 *>(rp + j);
+                                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+                            }
+                        }
+                    }
+                    if (out_f32) {
+                        float *op = reinterpret_cast<float *>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j < p.N) *reinterpret_cast<float4 *>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    } else {
+                        __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (col0 + j < p.N) {
+                                uint4 u;
+                                u.x = pack_bf16x2(v[j], v[j + 1]);
+                                u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                                u.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                                u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                                *reinterpret_cast<uint4 *>(op + j) = u;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == kAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// -------------------------------------------------------------------------- bring-up cross-check (CUDA cores)
+// Plain shared-memory tiled GEMM with the same epilogue; used only by tests / SFB_GEMM_IMPL=1 to tell a tcgen05
+// bug from a model-assembly bug.  Not on the product path.
+__global__ void __launch_bounds__(256) gemm_bf16_simple_kernel(const __nv_bfloat16 *A, int64_t lda, const __nv_bfloat16 *W, EpiParams p) {
+    __shared__ float sa[64][33];
+    __shared__ float sw[64][33];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < p.K; k0 += 32) {
+        for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+            const int r = i >> 5, c = i & 31;
+            const int gm = m0 + r, gn = n0 + r, gk = k0 + c;
+            sa[r][c] = (gm < p.M && gk < p.K) ? __bfloat162float(A[static_cast<int64_t>(gm) * lda + gk]) : 0.f;
+            sw[r][c] = (gn < p.N && gk < p.K) ? __bfloat162float(W[static_cast<int64_t>(gn) * p.K + gk]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sa[ty * 4 + i][k], b[i] = sw[tx * 4 + i][k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= p.M) continue;
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= p.N) continue;
+            float v = acc[i][j] + (p.bias ? p.bias[gn] : 0.f);
+            if (p.flags & SFB_GEMM_GELU) v = gelu_erf(v);
+            if (p.flags & SFB_GEMM_RESIDUAL) v += p.residual[static_cast<int64_t>(gm) * p.ldr + gn];
+            if (p.flags & SFB_GEMM_OUT_F32)
+                reinterpret_cast<float *>(p.out)[static_cast<int64_t>(gm) * p.ldo + gn] = v;
+            else
+                reinterpret_cast<__nv_bfloat16 *>(p.out)[static_cast<int64_t>(gm) * p.ldo + gn] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2D bf16 row-major (rows x cols, row stride ld elements) -> box (box_rows x 64 cols), 128B swizzle, zero OOB fill
+static int make_tmap(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return SFB_E_CUDA;
+    }
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld cols %lld ld %lld)", static_cast<int>(r),
+                  static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld));
+        return SFB_E_CUDA;
+    }
+    return SFB_OK;
+}
+
+}  // namespace gemm
+}  // namespace sfb
+
+extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const float *bias, const float *residual, int64_t ldr,
+                             void *out, int64_t ldo, int M, int N, int K, int flags, int impl, void *stream) {
+    using namespace sfb;
+    using namespace sfb::gemm;
+    SFB_CHECK_ARG(A && W && out, "sfb_gemm_bf16: null pointer");
+    SFB_CHECK_ARG(M > 0 && N > 0 && K > 0, "sfb_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+    SFB_CHECK_ARG(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0 && lda >= K && ldo >= N,
+                  "sfb_gemm_bf16: K, N, lda, ldo must be multiples of 8 (K=%d N=%d lda=%lld ldo=%lld)", K, N, (long long)lda,
+                  (long long)ldo);
+    SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                  "sfb_gemm_bf16: A, W, out must be 16-byte aligned");
+    if (flags & SFB_GEMM_RESIDUAL) {
+        SFB_CHECK_ARG(residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && ldr % 4 == 0,
+                      "sfb_gemm_bf16: residual must be non-null, 16-byte aligned, ldr %% 4 == 0");
+    }
+    SFB_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "sfb_gemm_bf16: bias must be 16-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    EpiParams p;
+    p.bias = bias, p.residual = residual, p.ldr = ldr, p.out = out, p.ldo = ldo;
+    p.M = M, p.N = N, p.K = K, p.flags = flags;
+    p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+
+    if (impl == 1) {
+        dim3 grid((N + 63) / 64, (M + 63) / 64);
+        gemm_bf16_simple_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(A), lda,
+                                                       reinterpret_cast<const __nv_bfloat16 *>(W), p);
+        SFB_CHECK_LAUNCH();
+        return SFB_OK;
+    }
+    SFB_CHECK_ARG(impl == 0, "sfb_gemm_bf16: unknown impl %d", impl);
+
+    CUtensorMap tmap_a, tmap_w;
+    int rc = make_tmap(&tmap_a, A, M, K, lda, BLOCK_M);
+    if (rc != SFB_OK) return rc;
+    rc = make_tmap(&tmap_w, W, N, K, K, BLOCK_N);
+    if (rc != SFB_OK) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    gemm_bf16_tcgen05_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tmap_a, tmap_w, p);
+    SFB_CHECK_LAUNCH();
+    return SFB_OK;
+}

@@ -1,0 +1,107 @@
+// K1: mel front-end on the GPU (the reference runs it in CPU dataloader workers through torchaudio).
+//   dataset/transforms.py:815-823  MelSpectrogram(sr 16 kHz, n_fft 1024, win 400, hop 160, 128 mels, power 2)
+//   dataset/transforms.py:826-834  log(x + 1e-6)
+//   dataset/transforms.py:836-858  pad time 65 -> 66 with 0.0 (log domain, before normalisation)
+//   dataset/transforms.py:861-871  (x - (-4.2677393)) / (2 * 4.5689974)
+// One CTA per (segment, STFT frame).  The periodic Hann(400) window sits at samples [312, 712) of the 1024-sample
+// frame, so only 400 products per bin are non-zero: a direct 400-term DFT for bins 0..512 with a 1024-entry
+// twiddle table in shared memory, accumulated in fp64 (a pure tone leaves most bins ~1e-8 of the peak, and
+// log(x + 1e-6) exposes fp32 summation error there).  |X|^2 is invariant to the 312-sample phase offset.
+// The 513 x 128 HTK triangle filterbank (L2-resident, 262 KB) is applied from shared-memory power values.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace sfb {
+namespace mel {
+
+constexpr int N_FFT = 1024, WIN = 400, HOP = 160, N_FREQ = 513, N_MEL = 128, N_FRAMES = 65, T_OUT = 66, SEG = 10240;
+constexpr int WIN_OFF = (N_FFT - WIN) / 2;  // 312
+constexpr float LOG_EPS = 1e-6f, NORM_MEAN = -4.2677393f, NORM_STD = 4.5689974f;
+
+__device__ double2 g_twiddle[N_FFT];       // (cos, sin)(2 pi j / 1024)
+__device__ float g_window[WIN];
+__device__ float g_fb[N_FREQ * N_MEL];     // [freq][mel]
+
+__global__ void __launch_bounds__(256) mel_kernel(const float *__restrict__ wave, float *__restrict__ out) {
+    __shared__ double2 tw[N_FFT];
+    __shared__ float xs[WIN];
+    __shared__ float pw[N_FREQ + 3];
+    const int frame = blockIdx.x % N_FRAMES;
+    const int64_t seg = blockIdx.x / N_FRAMES;
+    const int tid = threadIdx.x;
+    for (int j = tid; j < N_FFT; j += 256) tw[j] = g_twiddle[j];
+    const float *w = wave + seg * SEG;
+    for (int n = tid; n < WIN; n += 256) {
+        int idx = frame * HOP + WIN_OFF + n - N_FFT / 2;          // index into the un-padded segment
+        idx = idx < 0 ? -idx : (idx >= SEG ? 2 * (SEG - 1) - idx : idx);   // reflect padding (torch.stft center=True)
+        xs[n] = __ldg(w + idx) * g_window[n];
+    }
+    __syncthreads();
+    for (int k = tid; k < N_FREQ; k += 256) {
+        double re = 0.0, im = 0.0;
+#pragma unroll 4
+        for (int n = 0; n < WIN; ++n) {
+            const double2 c = tw[(k * n) & (N_FFT - 1)];
+            const double x = static_cast<double>(xs[n]);
+            re = fma(x, c.x, re);
+            im = fma(x, c.y, im);
+        }
+        pw[k] = static_cast<float>(re * re + im * im);
+    }
+    __syncthreads();
+    if (tid < N_MEL) {
+        float acc = 0.f;
+        for (int k = 0; k < N_FREQ; ++k) acc = fmaf(pw[k], __ldg(g_fb + k * N_MEL + tid), acc);
+        float *o = out + (seg * N_MEL + tid) * T_OUT;
+        o[frame] = (logf(acc + LOG_EPS) - NORM_MEAN) / (2.0f * NORM_STD);
+        if (frame == 0) o[T_OUT - 1] = (0.0f - NORM_MEAN) / (2.0f * NORM_STD);
+    }
+}
+
+static int init_tables() {
+    static bool done = false;
+    if (done) return SFB_OK;
+    static double2 tw[N_FFT];
+    static float win[WIN];
+    static float fb[N_FREQ * N_MEL];
+    const double pi = 3.14159265358979323846;
+    for (int j = 0; j < N_FFT; ++j) tw[j] = make_double2(cos(2.0 * pi * j / N_FFT), sin(2.0 * pi * j / N_FFT));
+    for (int n = 0; n < WIN; ++n) win[n] = static_cast<float>(0.5 - 0.5 * cos(2.0 * pi * n / WIN));   // periodic Hann
+    // torchaudio.functional.melscale_fbanks(513, 0, 8000, 128, 16000, norm=None, mel_scale='htk')
+    auto hz2mel = [](double f) { return 2595.0 * log10(1.0 + f / 700.0); };
+    double fpts[N_MEL + 2];
+    const double m_lo = hz2mel(0.0), m_hi = hz2mel(8000.0);
+    for (int i = 0; i < N_MEL + 2; ++i) {
+        const double m = m_lo + (m_hi - m_lo) * i / (N_MEL + 1);
+        fpts[i] = 700.0 * (pow(10.0, m / 2595.0) - 1.0);
+    }
+    for (int k = 0; k < N_FREQ; ++k) {
+        const double f = 8000.0 * k / (N_FREQ - 1);
+        for (int m = 0; m < N_MEL; ++m) {
+            const double down = (f - fpts[m]) / (fpts[m + 1] - fpts[m]);
+            const double up = (fpts[m + 2] - f) / (fpts[m + 2] - fpts[m + 1]);
+            const double v = fmin(down, up);
+            fb[k * N_MEL + m] = static_cast<float>(v > 0.0 ? v : 0.0);
+        }
+    }
+    SFB_CHECK_CUDA(cudaMemcpyToSymbol(g_twiddle, tw, sizeof(tw)));
+    SFB_CHECK_CUDA(cudaMemcpyToSymbol(g_window, win, sizeof(win)));
+    SFB_CHECK_CUDA(cudaMemcpyToSymbol(g_fb, fb, sizeof(fb)));
+    done = true;
+    return SFB_OK;
+}
+
+}  // namespace mel
+}  // namespace sfb
+
+extern "C" int sfb_mel_frontend(const float *wave, float *out, int n_seg, void *stream) {
+    using namespace sfb;
+    using namespace sfb::mel;
+    SFB_CHECK_ARG(wave && out && n_seg > 0, "sfb_mel_frontend: bad arguments");
+    int rc = init_tables();   // first call only: three small host->device table uploads
+    if (rc != SFB_OK) return rc;
+    mel_kernel<<<static_cast<unsigned>(static_cast<int64_t>(n_seg) * N_FRAMES), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wave, out);
+    SFB_CHECK_LAUNCH();
+    return SFB_OK;
+}

@@ -1,0 +1,202 @@
+"""Thin tensor-level wrappers over the C-ABI.  PyTorch is used for device memory and streams only.
+
+Every function launches asynchronously on the current CUDA stream of the tensors' device and fails loudly
+(`SfbError`) if the library is missing or an argument is rejected; there is no fallback implementation.
+"""
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AttnDesc, SFB_GEMM_GELU, SFB_GEMM_OUT_F32, SFB_GEMM_RESIDUAL, check
+
+D = 768
+
+# bring-up switches (tests only): SFB_GEMM_IMPL=1 / SFB_ATTN_IMPL=1 route through the plain CUDA-core kernels
+GEMM_IMPL = int(os.environ.get('SFB_GEMM_IMPL', '0'))
+ATTN_IMPL = int(os.environ.get('SFB_ATTN_IMPL', '0'))
+
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of kernel launches issued through this module since import (bench.py reports the delta)."""
+    return _launches
+
+
+def _stream(t: torch.Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _count(n: int = 1):
+    global _launches
+    _launches += n
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.SfbError(f'{name} must be a CUDA tensor: synchformer_b200 has no CPU path')
+
+
+def device_check():
+    check(_lib.load().sfb_device_check(), 'sfb_device_check')
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None, *, gelu: bool = False,
+         residual: Optional[torch.Tensor] = None, out_f32: bool = False, impl: Optional[int] = None) -> torch.Tensor:
+    """out = epi(a @ w.T + bias).  a (M, K) bf16 (row stride may exceed K), w (N, K) bf16 contiguous, bias (N,) fp32,
+    residual (M, N) or (1, N) fp32 (broadcast)."""
+    require_cuda(a, 'a')
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == (torch.float32 if out_f32 else torch.bfloat16)
+    flags = (SFB_GEMM_GELU if gelu else 0) | (SFB_GEMM_OUT_F32 if out_f32 else 0)
+    ldr = 0
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(-1) == 1 and residual.shape[-1] == N
+        flags |= SFB_GEMM_RESIDUAL
+        ldr = 0 if residual.numel() == N else residual.stride(0)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    check(_lib.load().sfb_gemm_bf16(_p(a), a.stride(0), _p(w), _p(bias), _p(residual), ldr, _p(out), out.stride(0), M, N, K, flags,
+                                    GEMM_IMPL if impl is None else impl, _stream(a)), 'sfb_gemm_bf16')
+    _count()
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None, *,
+              rows: Optional[int] = None, group: Optional[int] = None, group_stride: Optional[int] = None, offset: int = 0,
+              gamma2: Optional[torch.Tensor] = None, beta2: Optional[torch.Tensor] = None, eps2: float = 0.0,
+              out_f32: bool = False) -> torch.Tensor:
+    """Row LayerNorm over 768 of fp32 x (R, 768).  Output row r reads input row (r // group) * group_stride + offset + r % group."""
+    require_cuda(x, 'x')
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == D and x.stride(1) == 1
+    if rows is None:
+        rows = x.shape[0]
+    if group is None:
+        group, group_stride = rows, rows
+    assert ((rows - 1) // group) * group_stride + offset + (rows - 1) % group < x.shape[0], 'row gather out of range'
+    if out is None:
+        out = torch.empty((rows, D), device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    assert out.shape[0] >= rows and out.shape[1] == D and out.stride(1) == 1
+    assert out.dtype == (torch.float32 if out_f32 else torch.bfloat16)
+    check(_lib.load().sfb_layernorm(_p(x), x.stride(0), _p(out), out.stride(0), int(out_f32), _p(gamma), _p(beta), eps, _p(gamma2), _p(beta2),
+                                    eps2, rows, group, group_stride, offset, _stream(x)), 'sfb_layernorm')
+    _count()
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, q_strides, kv_strides, o_strides, n_outer: int,
+              n_inner: int, n_heads: int, head_dim: int, Lq: int, Lk: int, scale: float, k_prefix: Optional[torch.Tensor] = None,
+              v_prefix: Optional[torch.Tensor] = None, prefix_outer: int = 0, impl: Optional[int] = None):
+    """softmax(scale q k^T) v on strided bf16 views; q/k/v/out are tensors whose data_ptr() is the address of problem
+    (0, 0), head 0, row 0; *_strides = (outer, inner, row) in elements.  See sfb_attn_desc in the header."""
+    require_cuda(q, 'q')
+    for t in (q, k, v, out):
+        assert t.dtype == torch.bfloat16
+    d = AttnDesc()
+    d.q, d.k, d.v, d.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    d.k_prefix = None if k_prefix is None else k_prefix.data_ptr()
+    d.v_prefix = None if v_prefix is None else v_prefix.data_ptr()
+    d.q_outer, d.q_inner, d.q_row = q_strides
+    d.kv_outer, d.kv_inner, d.kv_row = kv_strides
+    d.o_outer, d.o_inner, d.o_row = o_strides
+    d.prefix_outer = prefix_outer
+    d.n_outer, d.n_inner, d.n_heads, d.head_dim, d.Lq, d.Lk = n_outer, n_inner, n_heads, head_dim, Lq, Lk
+    d.scale = scale
+    d.impl = ATTN_IMPL if impl is None else impl
+    check(_lib.load().sfb_attention(ctypes.byref(d), _stream(q)), 'sfb_attention')
+    _count()
+
+
+_VIDEO_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.uint8: 3}
+
+
+def im2col_video(vis: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """vis (n_seg, 16, 3, 224, 224) fp32 / fp16 / bf16 / uint8 contiguous -> (n_seg * 1568, 1536) bf16."""
+    require_cuda(vis, 'vis')
+    assert vis.is_contiguous() and tuple(vis.shape[1:]) == (16, 3, 224, 224), f'bad video shape {tuple(vis.shape)}'
+    if vis.dtype not in _VIDEO_DTYPES:
+        raise _lib.SfbError(f'unsupported video dtype {vis.dtype}')
+    n = vis.shape[0]
+    if out is None:
+        out = torch.empty((n * 1568, 1536), device=vis.device, dtype=torch.bfloat16)
+    check(_lib.load().sfb_im2col_video(_p(vis), _VIDEO_DTYPES[vis.dtype], _p(out), n, _stream(vis)), 'sfb_im2col_video')
+    _count()
+    return out
+
+
+def video_tokens(patch: torch.Tensor, cls_token: torch.Tensor, pos_embed: torch.Tensor, temp_embed: torch.Tensor, n_seg: int,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((n_seg * 1569, D), device=patch.device, dtype=torch.float32)
+    check(_lib.load().sfb_video_tokens(_p(patch), _p(cls_token), _p(pos_embed), _p(temp_embed), _p(out), n_seg, _stream(patch)),
+          'sfb_video_tokens')
+    _count()
+    return out
+
+
+def im2col_ast(spec: torch.Tensor) -> torch.Tensor:
+    """spec (n_seg, 128, 66) fp32 contiguous [freq, time] -> (n_seg * 72, 256) bf16."""
+    require_cuda(spec, 'spec')
+    assert spec.dtype == torch.float32 and spec.is_contiguous() and tuple(spec.shape[1:]) == (128, 66), f'bad mel shape {tuple(spec.shape)}'
+    n = spec.shape[0]
+    out = torch.empty((n * 72, 256), device=spec.device, dtype=torch.bfloat16)
+    check(_lib.load().sfb_im2col_ast(_p(spec), _p(out), n, _stream(spec)), 'sfb_im2col_ast')
+    _count()
+    return out
+
+
+def ast_tokens(patch: torch.Tensor, cls_token: torch.Tensor, dist_token: torch.Tensor, pos_embed: torch.Tensor, n_seg: int) -> torch.Tensor:
+    out = torch.empty((n_seg * 74, D), device=patch.device, dtype=torch.float32)
+    check(_lib.load().sfb_ast_tokens(_p(patch), _p(cls_token), _p(dist_token), _p(pos_embed), _p(out), n_seg, _stream(patch)), 'sfb_ast_tokens')
+    _count()
+    return out
+
+
+def sync_tokens(v: torch.Tensor, a: torch.Tensor, vis_ln_w, vis_ln_b, aud_ln_w, aud_ln_b, eps: float, off_tok, mod_tok, pos_emb, B: int,
+                S: int) -> torch.Tensor:
+    out = torch.empty((B * (2 + 14 * S), D), device=v.device, dtype=torch.float32)
+    check(_lib.load().sfb_sync_tokens(_p(v), _p(a), _p(vis_ln_w), _p(vis_ln_b), _p(aud_ln_w), _p(aud_ln_b), eps, _p(off_tok), _p(mod_tok),
+                                      _p(pos_emb), _p(out), B, S, _stream(v)), 'sfb_sync_tokens')
+    _count()
+    return out
+
+
+def sync_head(x: torch.Tensor, T: int, ln_w, ln_b, eps: float, W: torch.Tensor, b: torch.Tensor, B: int) -> torch.Tensor:
+    n_cls = W.shape[0]
+    out = torch.empty((B, n_cls), device=x.device, dtype=torch.float32)
+    check(_lib.load().sfb_sync_head(_p(x), T, _p(ln_w), _p(ln_b), eps, _p(W), _p(b), _p(out), B, n_cls, _stream(x)), 'sfb_sync_head')
+    _count()
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, 'x')
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() % 4 == 0
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().sfb_cast_f32_bf16(_p(x), _p(out), x.numel(), _stream(x)), 'sfb_cast_f32_bf16')
+    _count()
+    return out
+
+
+def mel_frontend(wave: torch.Tensor) -> torch.Tensor:
+    """wave (..., 10240) fp32 -> normalised log-mel (..., 128, 66) fp32 (dataset/transforms.py:815-871)."""
+    require_cuda(wave, 'wave')
+    assert wave.dtype == torch.float32 and wave.is_contiguous() and wave.shape[-1] == 10240
+    n = wave.numel() // 10240
+    out = torch.empty((*wave.shape[:-1], 128, 66), device=wave.device, dtype=torch.float32)
+    check(_lib.load().sfb_mel_frontend(_p(wave), _p(out), n, _stream(wave)), 'sfb_mel_frontend')
+    _count()
+    return out

@@ -1,0 +1,314 @@
+"""GPU: every kernel of the C-ABI against a plain PyTorch fp32 restatement of the same op on the same (bf16-rounded) inputs."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    # M, N, K            (tails in M, N and K; 1-row; every (N, K) the model uses)
+    (1, 2304, 768), (77, 768, 768), (128, 256, 64), (300, 768, 768), (1000, 2304, 768), (1569 * 2, 768, 3072),
+    (513, 3072, 768), (3137, 768, 1536), (144, 768, 256), (260, 1536, 768), (130, 40, 72), (4096, 768, 768),
+]
+
+
+@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(1, id='simple')])
+@pytest.mark.parametrize('M,N,K', GEMM_SHAPES)
+def test_gemm_bias(cuda_device, impl, M, N, K):
+    from synchformer_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(M * 7 + N * 3 + K)
+    a = _bf(torch.randn(M, K, device='cuda', generator=g))
+    w = _bf(torch.randn(N, K, device='cuda', generator=g) * 0.05)
+    b = torch.randn(N, device='cuda', generator=g)
+    out = ops.gemm(a, w, b, impl=impl)
+    ref = a.float() @ w.float().T + b
+    torch.cuda.synchronize()
+    assert out.dtype == torch.bfloat16
+    assert rel_l2(out.float(), ref) < 4e-3          # bf16 output rounding: 2^-9 relative per element
+    assert (out.float() - ref).abs().max() <= 1e-2 * ref.abs().max() + 1e-3
+
+
+@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(1, id='simple')])
+def test_gemm_epilogues(cuda_device, impl):
+    from synchformer_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(3)
+    M, N, K = 1000, 768, 768
+    a = _bf(torch.randn(M, K, device='cuda', generator=g))
+    w = _bf(torch.randn(N, K, device='cuda', generator=g) * 0.05)
+    b = torch.randn(N, device='cuda', generator=g)
+    res = torch.randn(M, N, device='cuda', generator=g)
+    lin = a.float() @ w.float().T + b
+    # fp32 output, no rounding of the result: tight tolerance pins accumulation + bias
+    out = ops.gemm(a, w, b, out_f32=True, impl=impl)
+    assert rel_l2(out, lin) < 2e-6
+    out = ops.gemm(a, w, None, out_f32=True, impl=impl)
+    assert rel_l2(out, lin - b) < 2e-6
+    # exact-erf GELU
+    out = ops.gemm(a, w, b, gelu=True, out_f32=True, impl=impl)
+    assert rel_l2(out, torch.nn.functional.gelu(lin)) < 5e-6
+    # residual, in place on the fp32 stream
+    x = res.clone()
+    ops.gemm(a, w, b, out=x, residual=x, out_f32=True, impl=impl)
+    assert rel_l2(x, lin + res) < 2e-6
+    # broadcast residual row (aggregator CLS token)
+    out = ops.gemm(a, w, b, residual=res[:1].contiguous(), out_f32=True, impl=impl)
+    assert rel_l2(out, lin + res[:1]) < 2e-6
+    # strided A (a column block of a wider activation) and strided output
+    wide = _bf(torch.randn(M, 3 * K, device='cuda', generator=g))
+    dst = torch.zeros(M, 2 * N, device='cuda', dtype=torch.bfloat16)
+    ops.gemm(wide[:, K:2 * K], w, b, out=dst[:, N:], impl=impl)
+    assert rel_l2(dst[:, N:].float(), wide[:, K:2 * K].float() @ w.float().T + b) < 4e-3
+    assert float(dst[:, :N].abs().max()) == 0.0
+    torch.cuda.synchronize()
+
+
+def test_gemm_full_size_linearity_property(cuda_device):
+    """At the benchmark's row count (64 clips x 8 segments x 1569 tokens) the result cannot be compared with a CPU oracle in
+    seconds; use linearity instead: (A + A') W == A W + A' W up to fp32 accumulation order, on a strided sample of rows."""
+    from synchformer_b200 import ops
+    M, N, K = 64 * 8 * 1569, 768, 768
+    g = torch.Generator(device='cuda').manual_seed(11)
+    # small integers are exact in bf16 and their products/sums are exact in fp32 -> bit-exact property
+    a1 = torch.randint(-4, 5, (M, K), device='cuda', generator=g).to(torch.bfloat16)
+    a2 = torch.randint(-4, 5, (M, K), device='cuda', generator=g).to(torch.bfloat16)
+    w = torch.randint(-3, 4, (N, K), device='cuda', generator=g).to(torch.bfloat16)
+    y1 = ops.gemm(a1, w, None, out_f32=True)
+    y2 = ops.gemm(a2, w, None, out_f32=True)
+    y12 = ops.gemm((a1.float() + a2.float()).to(torch.bfloat16), w, None, out_f32=True)
+    assert torch.equal(y12, y1 + y2)
+    rows = torch.arange(0, M, 4099, device='cuda')
+    assert torch.equal(y1[rows], a1[rows].float() @ w.float().T)
+    assert torch.equal(y1[-3:], a1[-3:].float() @ w.float().T)        # the ragged last tile
+
+
+# -------------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize('eps', [1e-6, 1e-12, 1e-5])
+def test_layernorm(cuda_device, eps):
+    from synchformer_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randn(1003, 768, device='cuda', generator=g) * 3 + 0.5
+    w = torch.randn(768, device='cuda', generator=g)
+    b = torch.randn(768, device='cuda', generator=g)
+    ref = torch.nn.functional.layer_norm(x, (768,), w, b, eps)
+    out = ops.layernorm(x, w, b, eps, out_f32=True)
+    assert (out - ref).abs().max() < 2e-5
+    out = ops.layernorm(x, w, b, eps)
+    assert out.dtype == torch.bfloat16 and rel_l2(out.float(), ref) < 4e-3
+
+
+def test_layernorm_gather_and_double(cuda_device):
+    from synchformer_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(6)
+    n = 3
+    x = torch.randn(n * 1569, 768, device='cuda', generator=g)
+    w1, b1, w2, b2 = [torch.randn(768, device='cuda', generator=g) for _ in range(4)]
+    out = ops.layernorm(x, w1, b1, 1e-6, rows=n * 1568, group=1568, group_stride=1569, offset=1, gamma2=w2, beta2=b2, eps2=1e-6, out_f32=True)
+    src = x.view(n, 1569, 768)[:, 1:].reshape(-1, 768)
+    ref = torch.nn.functional.layer_norm(torch.nn.functional.layer_norm(src, (768,), w1, b1, 1e-6), (768,), w2, b2, 1e-6)
+    assert out.shape == (n * 1568, 768) and (out - ref).abs().max() < 5e-5
+
+
+# -------------------------------------------------------------------------------------------------- attention
+def _ref_attention(q, k, v, scale):
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    return torch.softmax(s, -1) @ v.float()
+
+
+@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(1, id='simple')])
+@pytest.mark.parametrize('mode', ['time', 'space', 'cls'])
+def test_divided_attention_views(cuda_device, impl, mode):
+    """Motionformer divided attention on the fused (n*1569, 2304) qkv layout (vit_helper.py:100-158)."""
+    from synchformer_b200 import ops
+    n, D = 2, 768
+    g = torch.Generator(device='cuda').manual_seed(17)
+    qkv = _bf(torch.randn(n * 1569, 3 * D, device='cuda', generator=g))
+    att = torch.zeros(n * 1569, D, device='cuda', dtype=torch.bfloat16)
+    row, seg = 3 * D, 1569 * 3 * D
+    t = qkv.float().view(n, 1569, 3, 12, 64)
+    q, k, v = t[:, :, 0].permute(0, 2, 1, 3), t[:, :, 1].permute(0, 2, 1, 3), t[:, :, 2].permute(0, 2, 1, 3)   # (n, h, 1569, 64)
+    if mode == 'cls':
+        ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], att, q_strides=(seg, 0, row), kv_strides=(seg, 0, row), o_strides=(1569 * D, 0, D),
+                      n_outer=n, n_inner=1, n_heads=12, head_dim=64, Lq=1, Lk=1569, scale=0.125, impl=impl)
+        ref = _ref_attention(q[:, :, :1], k, v, 0.125)                                    # (n, h, 1, 64)
+        got = att.view(n, 1569, 12, 64)[:, :1].permute(0, 2, 1, 3).float()
+    else:
+        q_, k_, v_ = [x[:, :, 1:].reshape(n, 12, 8, 196, 64) for x in (q, k, v)]
+        ck, cv = k[:, :, :1], v[:, :, :1]
+        if mode == 'time':
+            q_, k_, v_ = [x.permute(0, 1, 3, 2, 4) for x in (q_, k_, v_)]                 # (n, h, 196, 8, 64)
+            strides = dict(q_strides=(seg, row, 196 * row), kv_strides=(seg, row, 196 * row), o_strides=(1569 * D, D, 196 * D), n_inner=196, Lq=8, Lk=8)
+        else:
+            strides = dict(q_strides=(seg, 196 * row, row), kv_strides=(seg, 196 * row, row), o_strides=(1569 * D, 196 * D, D), n_inner=8, Lq=196, Lk=196)
+        G = q_.shape[2]
+        kk = torch.cat([ck.unsqueeze(2).expand(n, 12, G, 1, 64), k_], 3)
+        vv = torch.cat([cv.unsqueeze(2).expand(n, 12, G, 1, 64), v_], 3)
+        ref = _ref_attention(q_, kk, vv, 0.125)
+        if mode == 'time':
+            ref = ref.permute(0, 1, 3, 2, 4)
+        ref = ref.reshape(n, 12, 1568, 64)
+        ops.attention(qkv[1:], qkv[1:, D:], qkv[1:, 2 * D:], att[1:], n_outer=n, n_heads=12, head_dim=64, scale=0.125,
+                      k_prefix=qkv[:, D:], v_prefix=qkv[:, 2 * D:], prefix_outer=seg, impl=impl, **strides)
+        got = att.view(n, 1569, 12, 64)[:, 1:].permute(0, 2, 1, 3).float()
+        assert float(att.view(n, 1569, D)[:, 0].abs().max()) == 0.0                       # CLS rows untouched by this call
+    torch.cuda.synchronize()
+    assert rel_l2(got, ref) < 6e-3, mode
+    assert (got - ref).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(1, id='simple')])
+@pytest.mark.parametrize('L,heads,hd', [(74, 12, 64), (198, 8, 96), (114, 8, 96), (30, 8, 96), (16, 12, 64), (17, 12, 64)])
+def test_plain_self_attention(cuda_device, impl, L, heads, hd):
+    """AST (74 x 74, hd 64, modeling_ast.py:145-184) and sync (T x T, hd 96, modules/transformer.py:58-76) layouts."""
+    from synchformer_b200 import ops
+    B, D = 3, 768
+    g = torch.Generator(device='cuda').manual_seed(L)
+    qkv = _bf(torch.randn(B * L, 3 * D, device='cuda', generator=g) * 1.5)
+    att = torch.empty(B * L, D, device='cuda', dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(hd)
+    ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], att, q_strides=(L * 3 * D, 0, 3 * D), kv_strides=(L * 3 * D, 0, 3 * D), o_strides=(L * D, 0, D),
+                  n_outer=B, n_inner=1, n_heads=heads, head_dim=hd, Lq=L, Lk=L, scale=scale, impl=impl)
+    t = qkv.float().view(B, L, 3, heads, hd)
+    ref = _ref_attention(t[:, :, 0].permute(0, 2, 1, 3), t[:, :, 1].permute(0, 2, 1, 3), t[:, :, 2].permute(0, 2, 1, 3), scale)
+    got = att.view(B, L, heads, hd).permute(0, 2, 1, 3).float()
+    torch.cuda.synchronize()
+    assert rel_l2(got, ref) < 6e-3
+    assert (got - ref).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize('Lk,inner,row_rows', [(196, 8, 1), (12, 6, 6)])
+def test_aggregator_cls_query_attention(cuda_device, Lk, inner, row_rows):
+    """One shared CLS query per head against strided K/V groups plus a prefix CLS key/value (motionformer.py:301-334)."""
+    from synchformer_b200 import ops
+    n, D = 3, 768
+    rows_per_seg = Lk * inner
+    g = torch.Generator(device='cuda').manual_seed(Lk)
+    kv = _bf(torch.randn(n * rows_per_seg, 2 * D, device='cuda', generator=g))
+    cls_qkv = _bf(torch.randn(1, 3 * D, device='cuda', generator=g))
+    out = torch.empty(n * inner, D, device='cuda', dtype=torch.bfloat16)
+    inner_rows = Lk if row_rows == 1 else 1
+    ops.attention(cls_qkv, kv, kv[:, D:], out, q_strides=(0, 0, 0), kv_strides=(rows_per_seg * 2 * D, inner_rows * 2 * D, row_rows * 2 * D),
+                  o_strides=(inner * D, D, D), n_outer=n, n_inner=inner, n_heads=12, head_dim=64, Lq=1, Lk=Lk, scale=0.125,
+                  k_prefix=cls_qkv[:, D:], v_prefix=cls_qkv[:, 2 * D:], prefix_outer=0)
+    kvf = kv.float().view(n, rows_per_seg, 2, 12, 64)
+    if row_rows == 1:
+        grp = kvf.view(n, inner, Lk, 2, 12, 64)
+    else:
+        grp = kvf.view(n, Lk, inner, 2, 12, 64).permute(0, 2, 1, 3, 4, 5)
+    k = torch.cat([cls_qkv.float()[:, D:2 * D].view(1, 1, 1, 12, 64).expand(n, inner, 1, 12, 64), grp[:, :, :, 0]], 2).permute(0, 1, 3, 2, 4)
+    v = torch.cat([cls_qkv.float()[:, 2 * D:].view(1, 1, 1, 12, 64).expand(n, inner, 1, 12, 64), grp[:, :, :, 1]], 2).permute(0, 1, 3, 2, 4)
+    q = cls_qkv.float()[:, :D].view(1, 1, 12, 1, 64).expand(n, inner, 12, 1, 64)
+    ref = _ref_attention(q, k, v, 0.125).reshape(n * inner, D)
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), ref) < 6e-3
+
+
+# ------------------------------------------------------------------------------------- embeddings and tokens
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.bfloat16, torch.uint8])
+def test_im2col_video(cuda_device, dtype):
+    from synchformer_b200 import ops
+    n = 2
+    g = torch.Generator(device='cuda').manual_seed(1)
+    if dtype == torch.uint8:
+        vis = torch.randint(0, 256, (n, 16, 3, 224, 224), device='cuda', generator=g, dtype=torch.uint8)
+        visf = (vis.float() / 255.0 - 0.5) / 0.5                      # dataset/transforms.py:647-669
+    else:
+        vis = (torch.rand(n, 16, 3, 224, 224, device='cuda', generator=g) * 2 - 1).to(dtype)
+        visf = vis.float()
+    a = ops.im2col_video(vis)
+    ref = visf.view(n, 8, 2, 3, 14, 16, 14, 16).permute(0, 1, 4, 6, 3, 2, 5, 7).reshape(n * 1568, 1536)
+    torch.cuda.synchronize()
+    assert torch.equal(a, ref.to(torch.bfloat16))
+
+
+def test_patch_embed_equals_conv3d(cuda_device):
+    """im2col + GEMM + token assembly == Conv3d(k=s=(2,16,16)) + cls + separate pos-emb (vit_helper.py:436-445, video_model_builder.py:221-254)."""
+    from synchformer_b200 import ops
+    n = 2
+    g = torch.Generator(device='cuda').manual_seed(2)
+    vis = _bf(torch.rand(n, 16, 3, 224, 224, device='cuda', generator=g) * 2 - 1)
+    w = _bf(torch.randn(768, 3, 2, 16, 16, device='cuda', generator=g) * 0.03)
+    b, cls = torch.randn(768, device='cuda', generator=g), torch.randn(1, 1, 768, device='cuda', generator=g)
+    pos, tmp = torch.randn(1, 197, 768, device='cuda', generator=g), torch.randn(1, 8, 768, device='cuda', generator=g)
+    patch = ops.gemm(ops.im2col_video(vis), w.view(768, -1).contiguous(), b, out_f32=True)
+    x = ops.video_tokens(patch, cls, pos, tmp, n).view(n, 1569, 768)
+    conv = torch.nn.functional.conv3d(vis.float().permute(0, 2, 1, 3, 4), w.float(), b, stride=(2, 16, 16)).flatten(2).transpose(1, 2)
+    ref = torch.cat([cls.expand(n, 1, 768), conv], 1)
+    total = torch.cat([pos[:, :1], pos[:, 1:].repeat(1, 8, 1) + tmp.repeat_interleave(196, 1)], 1)
+    ref = ref + total
+    torch.cuda.synchronize()
+    assert rel_l2(x, ref) < 1e-5
+
+
+def test_ast_patch_embed_equals_conv2d(cuda_device):
+    from synchformer_b200 import ops
+    n = 3
+    g = torch.Generator(device='cuda').manual_seed(3)
+    spec = torch.randn(n, 128, 66, device='cuda', generator=g)
+    w = _bf(torch.randn(768, 1, 16, 16, device='cuda', generator=g) * 0.05)
+    b = torch.randn(768, device='cuda', generator=g)
+    cls, dist = torch.randn(1, 1, 768, device='cuda', generator=g), torch.randn(1, 1, 768, device='cuda', generator=g)
+    pos = torch.randn(1, 74, 768, device='cuda', generator=g)
+    a = ops.im2col_ast(spec)
+    patch = ops.gemm(a, w.view(768, 256).contiguous(), b, out_f32=True)
+    x = ops.ast_tokens(patch, cls, dist, pos, n).view(n, 74, 768)
+    conv = torch.nn.functional.conv2d(_bf(spec).float().unsqueeze(1), w.float(), b, stride=(10, 10)).flatten(2).transpose(1, 2)   # (n, 72, 768)
+    ref = torch.cat([cls.expand(n, 1, 768), dist.expand(n, 1, 768), conv], 1) + pos
+    torch.cuda.synchronize()
+    assert rel_l2(x, ref) < 1e-5
+
+
+def test_sync_tokens_and_head(cuda_device):
+    from synchformer_b200 import ops
+    B, S = 3, 4
+    T = 2 + 14 * S
+    g = torch.Generator(device='cuda').manual_seed(4)
+    r = lambda *s: torch.randn(*s, device='cuda', generator=g)
+    v, a = r(B, 8 * S, 768), r(B, 6 * S, 768)
+    vw, vb, aw, ab, off, mod, pos = r(768), r(768), r(768), r(768), r(1, 1, 768), r(1, 1, 768), r(1, T, 768)
+    x = ops.sync_tokens(v, a, vw, vb, aw, ab, 1e-5, off, mod, pos, B, S).view(B, T, 768)
+    ln = torch.nn.functional.layer_norm
+    ref = torch.cat([off.expand(B, 1, 768), ln(v, (768,), vw, vb, 1e-5), mod.expand(B, 1, 768), ln(a, (768,), aw, ab, 1e-5)], 1) + pos
+    assert (x - ref).abs().max() < 3e-5
+    lw, lb, W, bb = r(768), r(768), r(21, 768) * 0.05, r(21)
+    logits = ops.sync_head(x.view(B * T, 768), T, lw, lb, 1e-5, W, bb, B)
+    ref_logits = ln(ref[:, 0], (768,), lw, lb, 1e-5) @ W.T + bb
+    torch.cuda.synchronize()
+    assert (logits - ref_logits).abs().max() < 1e-4
+
+
+def test_cast(cuda_device):
+    from synchformer_b200 import ops
+    x = torch.randn(1000, 768, device='cuda')
+    assert torch.equal(ops.cast_bf16(x), x.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------ mel front-end
+def test_mel_frontend_against_oracle_and_reference_golden(cuda_device, golden_dir):
+    import os
+    from oracle import synchformer_oracle as O
+    from synchformer_b200 import ops, synth
+    wave = synth.synthetic_waveform(2, 2, 0)
+    mel = ops.mel_frontend(wave.cuda()).cpu()
+    assert mel.shape == (2, 2, 128, 66)
+    oracle = O.mel_frontend(wave).float()
+    golden = torch.from_numpy(np.load(os.path.join(golden_dir, 'mel_b2s2.npz'))['mel'])
+    # tolerance: the normalised log-mel spans about [-1.1, 1.3]; torchaudio's own fp32 FFT sits 2.3e-4 from the fp64 oracle
+    assert (mel - oracle).abs().max() < 5e-4
+    assert (mel - golden).abs().max() < 1e-3
+    # random (broadband) input exercises every bin and the reflect padding at both ends
+    g = torch.Generator().manual_seed(9)
+    noise = torch.randn(5, 10240, generator=g) * 0.3
+    assert (ops.mel_frontend(noise.cuda()).cpu() - O.mel_frontend(noise).float()).abs().max() < 5e-4

@@ -1,0 +1,143 @@
+"""GPU: the full forward path through the drop-in `Synchformer` class against the CPU oracle and the committed golden
+outputs of the reference, plus size-independent properties at the benchmark batch size.
+
+Tolerances (calibrated to the reference's own bf16-autocast path vs its fp32 path: features rel-L2 8.2e-3,
+logits max-abs 4.2e-3): offset-class argmax identical; logits max-abs <= 1e-2 and rel-L2 <= 5e-3; segment features rel-L2 <= 1e-2.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FEAT_TOL, LOGIT_ABS, LOGIT_REL = 1e-2, 1e-2, 5e-3
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope='module')
+def golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'sync_b2s2.npz'))
+    mel = np.load(os.path.join(golden_dir, 'mel_b2s2.npz'))['mel']
+    return g, torch.from_numpy(mel).unsqueeze(2)
+
+
+@pytest.fixture(scope='module')
+def model_s2(cuda_device):
+    from synchformer_b200 import model as M, synth
+    return M.build_synchformer(n_segments=2, state_dict=synth.synthetic_state_dict(1337, n_segments=2), device=cuda_device)
+
+
+def test_forward_matches_reference_golden(model_s2, golden):
+    from synchformer_b200 import synth
+    g, aud = golden
+    vis = synth.synthetic_video(2, 2, 0)
+    with torch.no_grad():
+        vf = model_s2.extract_vfeats(vis.cuda())
+        af = model_s2.extract_afeats(aud.cuda())
+        loss, logits = model_s2(vis.cuda(), aud.cuda(), torch.from_numpy(g['targets']).cuda())
+    torch.cuda.synchronize()
+    assert vf.shape == (2, 2, 8, 768) and af.shape == (2, 2, 6, 768) and logits.shape == (2, 21)
+    assert rel_l2(vf, g['vfeats']) <= FEAT_TOL, rel_l2(vf, g['vfeats'])
+    assert rel_l2(af, g['afeats']) <= FEAT_TOL, rel_l2(af, g['afeats'])
+    lg = logits.float().cpu().numpy()
+    assert np.abs(lg - g['logits']).max() <= LOGIT_ABS, np.abs(lg - g['logits']).max()
+    assert rel_l2(lg, g['logits']) <= LOGIT_REL
+    assert (lg.argmax(-1) == g['logits'].argmax(-1)).all()
+    assert abs(float(loss) - float(g['loss'])) < 5e-3
+    # inputs matter: the two clips' visual features differ by 16 % in the reference
+    assert rel_l2(vf[0], vf[1]) > 5e-2
+
+
+@pytest.mark.parametrize('video_dtype', [torch.float16, torch.uint8])
+def test_forward_matches_oracle_on_fresh_inputs(cuda_device, video_dtype):
+    """New weights / inputs (not the golden ones), fp16 video as RGBToHalfToZeroOne delivers it and raw uint8 frames (N2),
+    raw waveform through the GPU mel front-end; oracle run on the CPU in fp32 on the same tensors."""
+    from oracle import synchformer_oracle as O
+    from synchformer_b200 import model as M, ops, synth
+    B, S = 1, 3
+    sd = synth.synthetic_state_dict(99, n_segments=S)
+    model = M.build_synchformer(n_segments=S, state_dict=sd, device=cuda_device)
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (B, S, 16, 3, 224, 224), generator=g, dtype=torch.uint8)
+    vis_f = (u8.float() / 255.0 - 0.5) / 0.5
+    vis_in = u8 if video_dtype == torch.uint8 else vis_f.to(video_dtype)
+    vis_oracle = vis_f if video_dtype == torch.uint8 else vis_in.float()
+    wave = synth.synthetic_waveform(B, S, seed=1, freq_hz=523.25)
+    with torch.no_grad():
+        mel = ops.mel_frontend(wave.cuda())
+        _, logits = model(vis_in.cuda(), mel.unsqueeze(2))
+        vf = model.extract_vfeats(vis_in.cuda())
+    taps = {}
+    _, ref = O.forward(sd, vis_oracle, O.mel_frontend(wave).float().unsqueeze(2), taps=taps)
+    assert rel_l2(vf, taps['vfeats']) <= FEAT_TOL
+    assert (logits.cpu() - ref).abs().max() <= LOGIT_ABS
+    assert rel_l2(logits, ref) <= LOGIT_REL
+    assert torch.equal(logits.argmax(-1).cpu(), ref.argmax(-1))
+
+
+def test_bringup_kernels_agree_with_product_kernels(model_s2, golden):
+    """tcgen05 GEMM / tensor-core attention vs the plain CUDA-core cross-check kernels on the whole model."""
+    from synchformer_b200 import ops, synth
+    _, aud = golden
+    vis = synth.synthetic_video(2, 2, 0).cuda()
+    with torch.no_grad():
+        _, a = model_s2(vis, aud.cuda())
+        ops.GEMM_IMPL, ops.ATTN_IMPL = 1, 1
+        try:
+            _, b = model_s2(vis, aud.cuda())
+        finally:
+            ops.GEMM_IMPL, ops.ATTN_IMPL = 0, 0
+    assert (a - b).abs().max() < 5e-3
+    assert torch.equal(a.argmax(-1), b.argmax(-1))
+
+
+def test_batch_invariance_and_chunking_at_benchmark_scale(cuda_device):
+    """Config 2 of BASELINE.json (B = 64 clips x 8 segments): every clip's logits must equal, bit for bit, the logits of the
+    same clip run alone or with a different internal segment chunking (kernels are deterministic and batch-independent)."""
+    from synchformer_b200 import model as M, ops, synth
+    B, S = 64, 8
+    model = M.build_synchformer(n_segments=S, state_dict=synth.synthetic_state_dict(1337, n_segments=S), device=cuda_device)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    vis = (torch.rand(B, S, 16, 3, 224, 224, device='cuda', generator=g) * 2 - 1).half()
+    wave = torch.randn(B, S, 10240, device='cuda', generator=g) * 0.2
+    with torch.no_grad():
+        mel = ops.mel_frontend(wave).unsqueeze(2)
+        _, full = model(vis, mel)
+        model.vfeat_extractor.max_segments_per_pass = 96
+        _, chunked = model(vis, mel)
+        model.vfeat_extractor.max_segments_per_pass = 512
+        _, alone = model(vis[5:7], mel[5:7])
+    torch.cuda.synchronize()
+    assert full.shape == (B, 21) and torch.isfinite(full).all()
+    assert torch.equal(full, chunked)
+    assert torch.equal(full[5:7], alone)
+    assert full.std(0).mean() > 1e-3          # different clips give different logits
+
+
+def test_avclip_pooling_variant(cuda_device):
+    """segment_avclip.yaml encoders (agg_time_module='AveragePooling'): features are the time-mean of the sync.yaml ones."""
+    from synchformer_b200 import model as M, synth
+    sd = synth.synthetic_state_dict(5, n_segments=1)
+    base = M.build_synchformer(n_segments=1, state_dict=sd, device=cuda_device)
+    pooled = M.MotionFormer(extract_features=True, factorize_space_time=True, agg_space_module='TransformerEncoderLayer',
+                            agg_time_module='AveragePooling', add_global_repr=False).to(cuda_device).eval()
+    pooled.load_state_dict(base.vfeat_extractor.state_dict())
+    vis = synth.synthetic_video(1, 1, 3).cuda()
+    with torch.no_grad():
+        a = base.extract_vfeats(vis).mean(2)
+        b, _ = pooled(vis.permute(0, 1, 3, 2, 4, 5))
+    assert b.shape == (1, 1, 768) and torch.allclose(a, b, atol=1e-6)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from synchformer_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libsynchformer_b200.so')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        _lib.load()
