@@ -36,7 +36,7 @@ __device__ __forceinline__ void load8(const void *base, int64_t idx, float *f) {
         const uint2 u = __ldg(reinterpret_cast<const uint2 *>(base) + idx);
         const uint32_t w[2] = {u.x, u.y};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = (static_cast<float>((w[i >> 2] >> (8 * (i & 3))) & 0xffu) * (1.0f / 255.0f) - 0.5f) / 0.5f;
+        for (int i = 0; i < 8; ++i) f[i] = (__fdiv_rn(static_cast<float>((w[i >> 2] >> (8 * (i & 3))) & 0xffu), 255.0f) - 0.5f) / 0.5f;
     }
 }
 

@@ -8,7 +8,8 @@
 //   warp 1      MMA issuer     one thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16) per stage,
 //                              accumulating in TMEM; tcgen05.commit releases the stage ("empty") and, after the
 //                              last k-block, publishes the accumulator ("tmem_full")
-//   warps 2-9   epilogue       tcgen05.ld 32x32b.x32 (TMEM -> registers), bias / GELU / residual, vectorised stores;
+//   warps 2-9   epilogue       tcgen05.ld 32x32b.x32 (TMEM -> registers), bias / GELU, transpose through a swizzled per-warp
+//                              shared-memory buffer, then row-contiguous residual loads and 16-byte stores;
 //                              the 512 TMEM columns hold TWO 128x256 fp32 accumulators so the epilogue of tile i
 //                              overlaps the main loop of tile i+1
 // Tiles are walked n-fastest so the CTAs that share an A row-block run at the same time and hit it in L2;
@@ -17,6 +18,7 @@
 // Reference ops replaced: nn.Linear at vit_helper.py:105,156,393-396; modeling_ast.py:149-152,200,258,272;
 // modules/transformer.py:62-64,74,87-92; nn.TransformerEncoderLayer linears (motionformer.py:329); sync_model.py:55-56.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -34,7 +36,8 @@ constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
 constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 1024;  // + slack for 1024-byte alignment
+constexpr uint32_t EPI_WARP_BYTES = 4096;                        // 32 rows x 128 B transpose buffer per epilogue warp
+constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024;  // + slack for 1024-byte alignment
 constexpr uint32_t TMEM_COLS = 512;
 
 struct EpiParams {
@@ -46,6 +49,7 @@ struct EpiParams {
     int M, N, K;
     int flags;
     int num_m_blocks, num_n_blocks;
+    int m_fastest;   // tile walk order (experiment switch SFB_GEMM_ORDER=1); default n-fastest
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -185,8 +189,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.num_n_blocks) * BLOCK_M;
-                const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
+                const int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * BLOCK_M;
+                const int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = tiles_base + stage * STAGE_BYTES;
@@ -235,71 +239,116 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else {
         // ================================ epilogue ====================================
+        // TMEM -> registers (one accumulator row per thread) -> bias / GELU -> per-warp 4 KB shared-memory transpose buffer
+        // (16-byte chunks XOR-swizzled by row, conflict-free both ways) -> row-contiguous global access: every load/store
+        // instruction covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
         const int q = warp & 3;               // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
         const int half = (warp - 2) >> 2;     // which 128 of the 256 accumulator columns
         const bool gelu = (p.flags & SFB_GEMM_GELU) != 0;
         const bool has_res = (p.flags & SFB_GEMM_RESIDUAL) != 0;
         const bool out_f32 = (p.flags & SFB_GEMM_OUT_F32) != 0;
+        uint8_t *stage = smem_raw + (tiles_base - smem_u32(smem_raw)) + kStages * STAGE_BYTES + (warp - 2) * EPI_WARP_BYTES;
+        uint8_t *st_row = stage + lane * 128;                 // this thread's accumulator row in the transpose buffer
+        const int rr = lane >> 3, cc = lane & 7;              // read-back mapping: rows 4i + rr, 16-byte chunk cc
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / p.num_n_blocks) * BLOCK_M;
-            const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
-            const int row = m0 + q * 32 + lane;
+            const int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * BLOCK_M + q * 32;
+            const int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + half * 128;
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + half * 128);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            if (out_f32) {
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int col0 = n0 + half * 128 + c * 32;
-                uint32_t r[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + half * 128 + c * 32), r);
-                tmem_ld_wait();
-                if (row < p.M && col0 < p.N) {
-                    float v[32];
+                for (int c = 0; c < 4; ++c) {
+                    const int col0 = n0 + c * 32;
+                    uint32_t r[32];
+                    tmem_ld32(tbase + c * 32, r);
+                    tmem_ld_wait();
+                    if (col0 < p.N) {          // warp-uniform
+                        float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias != nullptr) {
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        if (p.bias != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N) {
-                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
-                                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+                            for (int j = 0; j < 32; j += 4) {
+                                if (col0 + j < p.N) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+                                    v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+                                }
                             }
                         }
-                    }
-                    if (gelu) {
+                        if (gelu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                    }
-                    if (has_res) {
-                        const float *rp = p.residual + static_cast<int64_t>(row) * p.ldr + col0;
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+                        }
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N) {
-                                const float4 b = *reinterpret_cast<const float4 *>(rp + j);
-                                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+                        for (int k = 0; k < 8; ++k)
+                            *reinterpret_cast<float4 *>(st_row + ((k ^ (lane & 7)) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                        __syncwarp();
+                        const int gcol = col0 + cc * 4;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rloc = 4 * i + rr;
+                            const int64_t grow = m0 + rloc;
+                            float4 val = *reinterpret_cast<const float4 *>(stage + rloc * 128 + ((cc ^ (rloc & 7)) << 4));
+                            if (grow < p.M && gcol < p.N) {
+                                if (has_res) {
+                                    const float4 b = *reinterpret_cast<const float4 *>(p.residual + grow * p.ldr + gcol);
+                                    val.x += b.x, val.y += b.y, val.z += b.z, val.w += b.w;
+                                }
+                                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + grow * p.ldo + gcol) = val;
                             }
                         }
+                        __syncwarp();
                     }
-                    if (out_f32) {
-                        float *op = reinterpret_cast<float *>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    const int col0 = n0 + c * 64;
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(tbase + c * 64, r0);
+                    tmem_ld32(tbase + c * 64 + 32, r1);
+                    tmem_ld_wait();
+                    if (col0 < p.N) {
+                        uint32_t packed[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N) *reinterpret_cast<float4 *>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        }
-                    } else {
-                        __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
+                        for (int hseg = 0; hseg < 2; ++hseg) {
+                            float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (col0 + j < p.N) {
-                                uint4 u;
-                                u.x = pack_bf16x2(v[j], v[j + 1]);
-                                u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                                u.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                                u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                                *reinterpret_cast<uint4 *>(op + j) = u;
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(hseg == 0 ? r0[j] : r1[j]);
+                            const int cb = col0 + hseg * 32;
+                            if (p.bias != nullptr) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    if (cb + j < p.N) {
+                                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + j));
+                                        v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+                                    }
+                                }
                             }
+                            if (gelu) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) packed[hseg * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
                         }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            *reinterpret_cast<uint4 *>(st_row + ((k ^ (lane & 7)) << 4)) = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                        __syncwarp();
+                        const int gcol = col0 + cc * 8;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rloc = 4 * i + rr;
+                            const int64_t grow = m0 + rloc;
+                            const uint4 val = *reinterpret_cast<const uint4 *>(stage + rloc * 128 + ((cc ^ (rloc & 7)) << 4));
+                            if (grow < p.M && gcol < p.N)
+                                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + grow * p.ldo + gcol) = val;
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -422,6 +471,7 @@ extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const fl
     SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                   "sfb_gemm_bf16: A, W, out must be 16-byte aligned");
+    SFB_CHECK_ARG(impl == 1 || !(flags & SFB_GEMM_RESIDUAL) || (flags & SFB_GEMM_OUT_F32), "sfb_gemm_bf16: RESIDUAL requires OUT_F32 (fp32 residual stream)");
     if (flags & SFB_GEMM_RESIDUAL) {
         SFB_CHECK_ARG(residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && ldr % 4 == 0,
                       "sfb_gemm_bf16: residual must be non-null, 16-byte aligned, ldr %% 4 == 0");
@@ -434,6 +484,8 @@ extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const fl
     p.M = M, p.N = N, p.K = K, p.flags = flags;
     p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+    static const int order_env = getenv("SFB_GEMM_ORDER") ? atoi(getenv("SFB_GEMM_ORDER")) : 0;
+    p.m_fastest = order_env;
 
     if (impl == 1) {
         dim3 grid((N + 63) / 64, (M + 63) / 64);

@@ -88,6 +88,16 @@ def main():
     print('relative difference between the two clips\' visual features:', float(d))
     assert d > 1e-2, 'inputs must influence the features'
 
+    # noise floor of the reference itself: its bf16-autocast path against its fp32 path on the same weights / inputs
+    # (SURVEY.md §8d calibrates the parity gates to this; stored so the tests can state the gate next to the floor)
+    with torch.autocast('cpu', dtype=torch.bfloat16):
+        vf16 = model.extract_vfeats(vis, for_loop=False).float()
+        af16 = model.extract_afeats(aud, for_loop=False).float()
+        lg16 = model(vis, aud)[1].float()
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    ref_bf16_noise = np.array([rel(vf16, vfeats), rel(af16, afeats), float((lg16 - logits).abs().max()), rel(lg16, logits)])
+    print('reference bf16-autocast vs fp32 [vfeats rel, afeats rel, logits max-abs, logits rel]:', ref_bf16_noise)
+
     names, cs = checksums(sd)
     os.chdir(cwd)
     np.savez_compressed(
@@ -95,7 +105,7 @@ def main():
         vfeats=vfeats.numpy(), afeats=afeats.numpy(), logits=logits.numpy(), loss=np.float32(loss),
         targets=targets.numpy(),
         **{k: sub(v) for k, v in taps.items()},
-        weight_checksum_names=np.array(names), weight_checksums=cs,
+        weight_checksum_names=np.array(names), weight_checksums=cs, ref_bf16_noise=ref_bf16_noise,
         meta=np.array([B, S, SEED_W, SEED_X, TAP_STRIDE_TOK, TAP_STRIDE_D]),
     )
     np.savez_compressed(os.path.join(HERE, 'mel_b2s2.npz'), mel=mel.numpy(),
