@@ -43,9 +43,11 @@ int sfb_device_check(void);
  * epilogue flags: SFB_GEMM_GELU      exact erf GELU (nn.GELU / HF GELUActivation)
  *                 SFB_GEMM_RESIDUAL  += residual[M,N] fp32 (row stride ldr; ldr == 0 broadcasts one row)
  *                 SFB_GEMM_OUT_F32   write fp32 instead of bf16 (out may alias residual)
- * tcgen05.mma (128x256x16 UMMA, fp32 accumulators in TMEM), TMA-fed 4-stage smem ring, persistent CTAs.
+ * tcgen05.mma (fp32 accumulators in TMEM), TMA-fed shared-memory ring, persistent CTAs; CTA pairs (cta_group::2,
+ * 256x256 tiles) for M > 128, single CTAs (128x256 tiles) otherwise.  RESIDUAL requires OUT_F32.
  * Requirements: K % 8 == 0, lda % 8 == 0, N % 8 == 0, ldo % 8 == 0, A/W 16-byte aligned.
- * `impl`: 0 = tcgen05 (product path); 1 = plain CUDA-core kernel kept only as a bring-up cross-check. */
+ * `impl`: 0 = product path (auto); 1 = plain CUDA-core kernel kept only as a bring-up cross-check;
+ *         2 / 3 = force the single-CTA / CTA-pair tcgen05 kernel (tests, A/B measurements). */
 #define SFB_GEMM_GELU 1
 #define SFB_GEMM_RESIDUAL 2
 #define SFB_GEMM_OUT_F32 4

@@ -8,8 +8,9 @@
 //   attn_time_kernel       Lq = Lk = 8 + CLS prefix, hd 64 (Motionformer time attention): one thread per (query frame,
 //                          head); the 8 lanes that share a (position, head) read the same K/V addresses, so the loads
 //                          broadcast and no shared memory or shuffles are needed.
-//   attn_generic_kernel<HD> one warp per query row, lanes split the head dim.  Used for single-query rows (Motionformer
-//                          CLS 1x1569, aggregator CLS 1x197 / 1x13) and as the bring-up cross-check for the other two.
+//   attn_row1_kernel       Lq = 1, hd 64 (Motionformer CLS query 1x1569, aggregator CLS rows 1x197 / 1x13): one CTA per problem,
+//                          8 lanes per key row, 32 private online-softmax states merged through shared memory.
+//   attn_generic_kernel<HD> one warp per query row, lanes split the head dim: the bring-up cross-check for the other three.
 // All keep scores and statistics in fp32; nothing is materialised in HBM (the reference materialises the attention
 // matrix and ~20 rearrange/cat copies per block: vit_helper.py:34-42,106-153; modeling_ast.py:156-176;
 // modules/transformer.py:67-70).
@@ -29,6 +30,13 @@ struct Desc {
     int n_outer, n_inner, n_heads, Lq, Lk;
     float scale;
 };
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float *f) {
+    f[0] = __uint_as_float(u.x << 16), f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16), f[3] = __uint_as_float(u.y & 0xffff0000u);
+    f[4] = __uint_as_float(u.z << 16), f[5] = __uint_as_float(u.z & 0xffff0000u);
+    f[6] = __uint_as_float(u.w << 16), f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
 
 // ------------------------------------------------------------------------------------------- generic kernel
 template <int HD>
@@ -98,12 +106,6 @@ __global__ void __launch_bounds__(256) attn_generic_kernel(const Desc d) {
 
 // ------------------------------------------------------------------------------ Motionformer time attention
 // lane = frame (0..7) + 8 * (head within a group of 4); a warp covers one (segment, position, head-group).
-__device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float *f) {
-    f[0] = __uint_as_float(u.x << 16), f[1] = __uint_as_float(u.x & 0xffff0000u);
-    f[2] = __uint_as_float(u.y << 16), f[3] = __uint_as_float(u.y & 0xffff0000u);
-    f[4] = __uint_as_float(u.z << 16), f[5] = __uint_as_float(u.z & 0xffff0000u);
-    f[6] = __uint_as_float(u.w << 16), f[7] = __uint_as_float(u.w & 0xffff0000u);
-}
 
 __global__ void __launch_bounds__(256) attn_time_kernel(const Desc d) {
     constexpr int HD = 64, L = 8;
@@ -171,6 +173,91 @@ __global__ void __launch_bounds__(256) attn_time_kernel(const Desc d) {
         u.z = pack_bf16x2(q[8 * c + 4], q[8 * c + 5]);
         u.w = pack_bf16x2(q[8 * c + 6], q[8 * c + 7]);
         op[c] = u;
+    }
+}
+
+// ------------------------------------------------------------------------------- single-query (CLS) kernel
+// Lq == 1, hd 64: one CTA of 256 threads per (outer, inner, head).  Eight lanes share a key row (16 bytes = 8 dims each, so one
+// load instruction covers 4 rows x 128 contiguous bytes), the 32 lane-groups of the CTA stride over the keys with a private
+// online softmax (3 shuffles per key), K and V of 4 keys in flight per lane, and the 32 partial (max, sum, acc) states are
+// merged through shared memory.  One pass over K and V: HBM-bound at large batch, latency-tolerant at small batch.
+__global__ void __launch_bounds__(256) attn_row1_kernel(const Desc d) {
+    constexpr int HD = 64, G = 32;           // lane groups per CTA
+    __shared__ float s_m[G], s_l[G];
+    __shared__ float s_acc[G][HD + 4];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int sub = lane & 7;                // which 8 dims of the row
+    const int grp = tid >> 3;                // 0..31
+    int pidx = blockIdx.x;
+    const int h = pidx % d.n_heads;
+    pidx /= d.n_heads;
+    const int i = pidx % d.n_inner;
+    const int o = pidx / d.n_inner;
+    const int Lkp = d.Lk + d.has_prefix;
+
+    float q[8];
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(d.q + o * d.q_outer + i * d.q_inner + h * HD) + sub), q);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] *= d.scale;
+    const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD + sub * 8;
+    const int64_t pre_base = o * d.prefix_outer + h * HD + sub * 8;
+
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    const int n_iter = (Lkp + 4 * G - 1) / (4 * G);      // CTA-uniform trip count: the shuffles below need every lane of the warp
+    for (int it = 0; it < n_iter; ++it) {
+        const int j0 = grp + it * 4 * G;
+        uint4 kk[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * G;
+            if (j < Lkp) {
+                const bool pre = d.has_prefix && j == 0;
+                const int64_t off = pre ? pre_base : kv_base + static_cast<int64_t>(j - d.has_prefix) * d.kv_row;
+                kk[u] = __ldg(reinterpret_cast<const uint4 *>((pre ? d.kp : d.k) + off));
+                vv[u] = __ldg(reinterpret_cast<const uint4 *>((pre ? d.vp : d.v) + off));
+            } else {
+                kk[u] = make_uint4(0, 0, 0, 0), vv[u] = make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float kf[8], vf[8];
+            bf16x8_to_f32(kk[u], kf);
+            float sdot = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sdot = fmaf(q[e], kf[e], sdot);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+            if (j0 + u * G < Lkp) {          // uniform within the 8-lane group
+                const float m_new = fmaxf(m, sdot);
+                const float corr = __expf(m - m_new), pj = __expf(sdot - m_new);
+                bf16x8_to_f32(vv[u], vf);
+                l = l * corr + pj;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf[e], acc[e] * corr);
+                m = m_new;
+            }
+        }
+    }
+    if (sub == 0) s_m[grp] = m, s_l[grp] = l;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_acc[grp][sub * 8 + e] = acc[e];
+    __syncthreads();
+    if (tid < HD) {
+        float M = -INFINITY;
+#pragma unroll 8
+        for (int g = 0; g < G; ++g) M = fmaxf(M, s_m[g]);
+        float L = 0.f, out = 0.f;
+#pragma unroll 8
+        for (int g = 0; g < G; ++g) {
+            const float w = s_m[g] == -INFINITY ? 0.f : __expf(s_m[g] - M);
+            L = fmaf(s_l[g], w, L);
+            out = fmaf(s_acc[g][tid], w, out);
+        }
+        d.out[o * d.o_outer + i * d.o_inner + h * HD + tid] = __float2bfloat16_rn(out / L);
     }
 }
 
@@ -410,6 +497,12 @@ extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
             }
             attn_mma_kernel<96><<<static_cast<unsigned>(n_prob), threads, mma_smem, st>>>(d, Lq_pad, Lk_pad);
         }
+        SFB_CHECK_LAUNCH();
+        return SFB_OK;
+    }
+    if (desc->impl == 0 && aligned16 && HD == 64 && d.Lq == 1) {
+        SFB_CHECK_ARG(n_prob < (1ll << 31), "sfb_attention: too many problems");
+        attn_row1_kernel<<<static_cast<unsigned>(n_prob), 256, 0, st>>>(d);
         SFB_CHECK_LAUNCH();
         return SFB_OK;
     }

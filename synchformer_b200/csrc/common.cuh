@@ -37,22 +37,58 @@ int num_sms();
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-// Exact-erf GELU for kernel epilogues: erfc via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e. fp32 round-off level;
-// measured max |gelu error| 4.7e-7 over [-12, 12]), branch-free, 2 MUFU + ~12 FMA-pipe instructions instead of erff's ~30.
-//   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2),   erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),  t = 1 / (1 + p z)
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-    const float ax = fabsf(x);
-    const float z = ax * 0.70710678118654752f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(t, poly, 1.421413741f);
-    poly = fmaf(t, poly, -0.284496736f);
-    poly = fmaf(t, poly, 0.254829592f);
-    poly *= t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-    return fmaxf(x, 0.0f) - 0.5f * ax * poly * e;
+// Exact-erf GELU for kernel epilogues, two elements per call on the packed fp32x2 pipe of sm_100 (FFMA2 / FMUL2).
+//   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2)
+//   erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),  t = 1 / (1 + p z)        (Abramowitz-Stegun 7.1.26,
+//   |erf error| <= 1.5e-7, i.e. fp32 round-off level; measured max |gelu error| 3.3e-7 over [-12, 12]).
+// With zs = |x| sqrt(log2(e) / 2): exp(-z^2) = 2^(-zs^2), p and the 0.5 are folded into the constants.  Branch-free;
+// per PAIR of elements: 4 MUFU (2 rcp, 2 ex2) + ~11 packed FMA-pipe instructions, against ~60 for two erff() calls.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void gelu_erf_fast2(float &x0, float &x1) {
+    const float a0 = fabsf(x0), a1 = fabsf(x1);
+    const uint64_t ax = pack_f32x2(a0, a1);
+    const uint64_t zs = mul_f32x2(ax, pack_f32x2(0.84932178f, 0.84932178f));
+    const uint64_t den = fma_f32x2(zs, pack_f32x2(0.27273747f, 0.27273747f), pack_f32x2(1.0f, 1.0f));
+    float d0, d1;
+    unpack_f32x2(den, d0, d1);
+    const uint64_t t = pack_f32x2(rcp_approx(d0), rcp_approx(d1));
+    uint64_t poly = fma_f32x2(t, pack_f32x2(0.53070271f, 0.53070271f), pack_f32x2(-0.72657603f, -0.72657603f));
+    poly = fma_f32x2(t, poly, pack_f32x2(0.71070689f, 0.71070689f));
+    poly = fma_f32x2(t, poly, pack_f32x2(-0.14224836f, -0.14224836f));
+    poly = fma_f32x2(t, poly, pack_f32x2(0.12741479f, 0.12741479f));
+    poly = mul_f32x2(poly, t);
+    float s0, s1;
+    unpack_f32x2(mul_f32x2(zs, zs), s0, s1);
+    const uint64_t e = pack_f32x2(ex2_approx(-s0), ex2_approx(-s1));
+    float h0, h1;
+    unpack_f32x2(mul_f32x2(mul_f32x2(ax, poly), e), h0, h1);
+    x0 = fmaxf(x0, 0.0f) - h0;
+    x1 = fmaxf(x1, 0.0f) - h1;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -32,11 +32,11 @@ __device__ __forceinline__ void load8(const void *base, int64_t idx, float *f) {
             const float2 t = unpack_bf16x2(w[i]);
             f[2 * i] = t.x, f[2 * i + 1] = t.y;
         }
-    } else {  // uint8 frames: /255 -> (x - 0.5) / 0.5   (dataset/transforms.py:647-669)
+    } else {  // uint8 frames: /255 -> (x - 0.5) / 0.5 = 2x/255 - 1 with a single rounding   (dataset/transforms.py:647-669)
         const uint2 u = __ldg(reinterpret_cast<const uint2 *>(base) + idx);
         const uint32_t w[2] = {u.x, u.y};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = (__fdiv_rn(static_cast<float>((w[i >> 2] >> (8 * (i & 3))) & 0xffu), 255.0f) - 0.5f) / 0.5f;
+        for (int i = 0; i < 8; ++i) f[i] = fmaf(static_cast<float>((w[i >> 2] >> (8 * (i & 3))) & 0xffu), 2.0f / 255.0f, -1.0f);
     }
 }
 

@@ -2,13 +2,20 @@
 //
 //   out[M,N] = epi( A[M,K] * W[N,K]^T + bias )          A, W bf16 K-major; fp32 accumulation
 //
-// sm_100a design (one persistent CTA per SM, 320 threads, warp-specialised):
-//   warp 0      TMA producer   cp.async.bulk.tensor 2D loads of a 128x64 A box and a 256x64 W box (128B swizzle)
-//                              into a 4-stage shared-memory ring, completion on "full" mbarriers
-//   warp 1      MMA issuer     one thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16) per stage,
+// sm_100a design (persistent CTAs, one per SM, 576 threads, warp-specialised).  Two instantiations of one template:
+//   CG = 2 (product path)  CTA PAIRS (cluster of 2) compute 256 x 256 tiles with tcgen05.mma.cta_group::2: each CTA stages its own
+//                          128 rows of A and HALF of the W tile (128 rows), so a pair moves 2/3 of the bytes per FLOP that two
+//                          independent 128 x 256 CTAs would.  Measured on B200: the single-CTA kernel saturates L2->SM bandwidth
+//                          (~6.4 KB/clk chip-wide) at ~50 % tensor-pipe activity, which is what makes the pairing pay.
+//                          5-stage ring of 32 KB stages; the pair leader issues the MMAs; commits are multicast to both CTAs.
+//   CG = 1                 single-CTA 128 x 256 tiles, 3-stage ring of 48 KB stages (small M, and kept for A/B comparison).
+// Roles:
+//   warp 0      TMA producer   cp.async.bulk.tensor 2D loads of a 128x64 A box and a (256 / CG)x64 W box (128B swizzle)
+//                              into the shared-memory ring, completion on the (leader's) "full" mbarriers
+//   warp 1      MMA issuer     one thread issues 4 x tcgen05.mma.kind::f16 (M 128*CG, N256, K16) per stage,
 //                              accumulating in TMEM; tcgen05.commit releases the stage ("empty") and, after the
 //                              last k-block, publishes the accumulator ("tmem_full")
-//   warps 2-9   epilogue       tcgen05.ld 32x32b.x32 (TMEM -> registers), bias / GELU, transpose through a swizzled per-warp
+//   warps 2-17  epilogue       tcgen05.ld 32x32b.x32 (TMEM -> registers), bias / GELU, transpose through a swizzled per-warp
 //                              shared-memory buffer, then row-contiguous residual loads and 16-byte stores;
 //                              the 512 TMEM columns hold TWO 128x256 fp32 accumulators so the epilogue of tile i
 //                              overlaps the main loop of tile i+1
@@ -29,16 +36,22 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
 constexpr int kAccStages = 2;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;  // 4 per TMEM lane quarter: the epilogue is latency-bound per warp, so it wants warps, not ILP
 constexpr int kThreads = 64 + kEpiWarps * 32;
-constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
-constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;               // 16 KB: this CTA's 128 rows of A
 constexpr uint32_t EPI_WARP_BYTES = 4096;                        // 32 rows x 128 B transpose buffer per epilogue warp
-constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024;  // + slack for 1024-byte alignment
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int kMaxStages = 6;
+
+template <int CG>
+struct Cfg {
+    static constexpr int kStages = CG == 2 ? 5 : 3;
+    static constexpr int B_ROWS = BLOCK_N / CG;                   // W rows staged by one CTA
+    static constexpr uint32_t B_BYTES = B_ROWS * BLOCK_K * 2;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB (pair) / 48 KB (single)
+    static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024;  // + 1024-byte alignment slack
+};
 
 struct EpiParams {
     const float *bias;
@@ -139,21 +152,68 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------ cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion may be signalled on the PEER CTA's mbarrier (pair leader's "full" barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap *m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit of all prior MMAs of the pair, arriving on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)   // 18 warps are allocated as 20 (granularity 4): 96 registers per thread
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const EpiParams p) {
+    using C = Cfg<CG>;
+    constexpr int kStages = C::kStages;
+    constexpr uint32_t STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kStages + 2 * kAccStages];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kAccStages];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;      // rank 0 of a pair is the MMA leader
     const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + kAccStages + a); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + kAccStages + a); };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -161,42 +221,58 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(full_bar(s), 1);     // the (leader's) producer arrive.expect_tx; TMA of both CTAs completes the bytes
+            mbar_init(empty_bar(s), 1);    // one tcgen05.commit (multicast to both CTAs when CG == 2)
         }
         for (int a = 0; a < kAccStages; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), kEpiWarps);
+            mbar_init(tempty_bar(a), kEpiWarps * CG);   // epilogue warps of every CTA of the pair arrive on the leader's barrier
         }
         fence_barrier_init();
     }
-    if (warp == 2) {  // one full warp allocates all 512 TMEM columns (1 CTA per SM) and later frees them
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 2) {  // one full warp per CTA allocates all 512 TMEM columns (1 CTA per SM) and later frees them
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // barriers initialised + TMEM allocated in both CTAs
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;       // tiles of (128 * CG) x 256
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * BLOCK_M;
-                const int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CG) + rank * BLOCK_M;
+                int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + rank * C::B_ROWS * (CG - 1);
+                // a box that lies completely outside the matrix (second CTA of a pair on a ragged edge) loads rows 0.. instead:
+                // its products only reach accumulator rows / columns that the epilogue masks
+                if (m0 >= p.M) m0 = 0;
+                if (n0 >= p.N) n0 = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = tiles_base + stage * STAGE_BYTES;
-                    mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-                    tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m0);
-                    tma_load_2d(sa + A_BYTES, &tmap_w, full_bar(stage), kb * BLOCK_K, n0);
+                    if (CG == 2) {
+                        const uint32_t fb = mapa_u32(full_bar(stage), 0);                     // the leader's barrier
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);   // bytes of both CTAs
+                        tma_load_2d_cg2(sa, &tmap_a, fb, kb * BLOCK_K, m0);
+                        tma_load_2d_cg2(sa + A_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+                        tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m0);
+                        tma_load_2d(sa + A_BYTES, &tmap_w, full_bar(stage), kb * BLOCK_K, n0);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
@@ -205,13 +281,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+        // ================================ MMA issuer (pair leader only) ================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M * CG, BLOCK_N);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // every epilogue warp (of both CTAs) has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -221,16 +297,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const uint32_t sb = sa + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        umma_bf16(tmem_d, make_sw128_desc(sa + k * UMMA_K * 2), make_sw128_desc(sb + k * UMMA_K * 2), idesc,
-                                  static_cast<uint32_t>((kb | k) != 0));
+                        const uint64_t da = make_sw128_desc(sa + k * UMMA_K * 2), db = make_sw128_desc(sb + k * UMMA_K * 2);
+                        if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, static_cast<uint32_t>((kb | k) != 0));
+                        else umma_bf16(tmem_d, da, db, idesc, static_cast<uint32_t>((kb | k) != 0));
                     }
-                    umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+                    if (CG == 2) umma_commit_cg2(empty_bar(stage)); else umma_commit(empty_bar(stage));   // smem stage reusable
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit(tfull_bar(acc));  // accumulator complete
+                if (CG == 2) umma_commit_cg2(tfull_bar(acc)); else umma_commit(tfull_bar(acc));           // accumulator complete
                 if (++acc == kAccStages) {
                     acc = 0;
                     acc_phase ^= 1u;
@@ -243,7 +320,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // (16-byte chunks XOR-swizzled by row, conflict-free both ways) -> row-contiguous global access: every load/store
         // instruction covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
         const int q = warp & 3;               // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
-        const int half = (warp - 2) >> 2;     // which 128 of the 256 accumulator columns
+        const int quarter = (warp - 2) >> 2;  // which 64 of the 256 accumulator columns
         const bool gelu = (p.flags & SFB_GEMM_GELU) != 0;
         const bool has_res = (p.flags & SFB_GEMM_RESIDUAL) != 0;
         const bool out_f32 = (p.flags & SFB_GEMM_OUT_F32) != 0;
@@ -252,16 +329,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int rr = lane >> 3, cc = lane & 7;              // read-back mapping: rows 4i + rr, 16-byte chunk cc
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * BLOCK_M + q * 32;
-            const int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + half * 128;
-            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + half * 128);
+        const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(tempty_bar(0), 0) : tempty_bar(0);
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            const int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CG) + rank * BLOCK_M + q * 32;
+            const int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + quarter * 64;
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + quarter * 64);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             if (out_f32) {
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     const int col0 = n0 + c * 32;
+                    const int gcol = col0 + cc * 4;
+                    // residual rows for the read-back mapping, requested before the accumulator is even read so that the
+                    // HBM latency overlaps the TMEM load, bias and GELU (explicit registers: `out` may alias `residual`,
+                    // so the compiler will not move these loads above the stores of the previous chunk by itself)
+                    float4 res[8];
+                    if (has_res && col0 < p.N) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int64_t grow = m0 + 4 * i + rr;
+                            res[i] = (grow < p.M && gcol < p.N) ? *reinterpret_cast<const float4 *>(p.residual + grow * p.ldr + gcol)
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
                     uint32_t r[32];
                     tmem_ld32(tbase + c * 32, r);
                     tmem_ld_wait();
@@ -280,23 +371,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         }
                         if (gelu) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+                            for (int j = 0; j < 32; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
                         }
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
                             *reinterpret_cast<float4 *>(st_row + ((k ^ (lane & 7)) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                         __syncwarp();
-                        const int gcol = col0 + cc * 4;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rloc = 4 * i + rr;
                             const int64_t grow = m0 + rloc;
                             float4 val = *reinterpret_cast<const float4 *>(stage + rloc * 128 + ((cc ^ (rloc & 7)) << 4));
                             if (grow < p.M && gcol < p.N) {
-                                if (has_res) {
-                                    const float4 b = *reinterpret_cast<const float4 *>(p.residual + grow * p.ldr + gcol);
-                                    val.x += b.x, val.y += b.y, val.z += b.z, val.w += b.w;
-                                }
+                                if (has_res) val.x += res[i].x, val.y += res[i].y, val.z += res[i].z, val.w += res[i].w;
                                 *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + grow * p.ldo + gcol) = val;
                             }
                         }
@@ -304,57 +391,54 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                 }
             } else {
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    const int col0 = n0 + c * 64;
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(tbase + c * 64, r0);
-                    tmem_ld32(tbase + c * 64 + 32, r1);
-                    tmem_ld_wait();
-                    if (col0 < p.N) {
-                        uint32_t packed[32];
+                const int col0 = n0;
+                if (col0 < p.N) {              // warp-uniform
 #pragma unroll
-                        for (int hseg = 0; hseg < 2; ++hseg) {
-                            float v[32];
+                    for (int hseg = 0; hseg < 2; ++hseg) {
+                        uint32_t r[32];
+                        tmem_ld32(tbase + hseg * 32, r);
+                        tmem_ld_wait();
+                        float v[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(hseg == 0 ? r0[j] : r1[j]);
-                            const int cb = col0 + hseg * 32;
-                            if (p.bias != nullptr) {
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        const int cb = col0 + hseg * 32;
+                        if (p.bias != nullptr) {
 #pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    if (cb + j < p.N) {
-                                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + j));
-                                        v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-                                    }
+                            for (int j = 0; j < 32; j += 4) {
+                                if (cb + j < p.N) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + j));
+                                    v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
                                 }
                             }
-                            if (gelu) {
+                        }
+                        if (gelu) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) packed[hseg * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                            for (int j = 0; j < 32; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
                         }
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            *reinterpret_cast<uint4 *>(st_row + ((k ^ (lane & 7)) << 4)) = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
-                        __syncwarp();
-                        const int gcol = col0 + cc * 8;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rloc = 4 * i + rr;
-                            const int64_t grow = m0 + rloc;
-                            const uint4 val = *reinterpret_cast<const uint4 *>(stage + rloc * 128 + ((cc ^ (rloc & 7)) << 4));
-                            if (grow < p.M && gcol < p.N)
-                                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + grow * p.ldo + gcol) = val;
-                        }
-                        __syncwarp();
+                        for (int k = 0; k < 4; ++k)      // 16-byte chunk hseg*4 + k of this thread's 128-byte row
+                            *reinterpret_cast<uint4 *>(st_row + (((hseg * 4 + k) ^ (lane & 7)) << 4)) =
+                                make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                           pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
                     }
+                    __syncwarp();
+                    const int gcol = col0 + cc * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rloc = 4 * i + rr;
+                        const int64_t grow = m0 + rloc;
+                        const uint4 val = *reinterpret_cast<const uint4 *>(stage + rloc * 128 + ((cc ^ (rloc & 7)) << 4));
+                        if (grow < p.M && gcol < p.N)
+                            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + grow * p.ldo + gcol) = val;
+                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+            }
             if (++acc == kAccStages) {
                 acc = 0;
                 acc_phase ^= 1u;
@@ -363,10 +447,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // nobody may still touch the peer's smem / TMEM / barriers
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -494,22 +579,46 @@ extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const fl
         SFB_CHECK_LAUNCH();
         return SFB_OK;
     }
-    SFB_CHECK_ARG(impl == 0, "sfb_gemm_bf16: unknown impl %d", impl);
+    SFB_CHECK_ARG(impl == 0 || impl == 2 || impl == 3, "sfb_gemm_bf16: unknown impl %d (0 auto, 1 CUDA-core check, 2 single-CTA, 3 CTA-pair)", impl);
+    // CTA pairs (256-row tiles) unless the problem has at most one 128-row block
+    const int cg = impl == 2 ? 1 : impl == 3 ? 2 : (M > BLOCK_M ? 2 : 1);
 
     CUtensorMap tmap_a, tmap_w;
     int rc = make_tmap(&tmap_a, A, M, K, lda, BLOCK_M);
     if (rc != SFB_OK) return rc;
-    rc = make_tmap(&tmap_w, W, N, K, K, BLOCK_N);
+    rc = make_tmap(&tmap_w, W, N, K, K, BLOCK_N / cg);
     if (rc != SFB_OK) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
+    if (cg == 1) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+            attr_set = true;
+        }
+        const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+        const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+        gemm_bf16_tcgen05_kernel<1><<<grid, kThreads, Cfg<1>::SMEM_BYTES, st>>>(tmap_a, tmap_w, p);
+        SFB_CHECK_LAUNCH();
+        return SFB_OK;
     }
+    static bool attr_set2 = false;
+    if (!attr_set2) {
+        SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+        attr_set2 = true;
+    }
+    p.num_m_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);             // 256-row pair tiles
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    gemm_bf16_tcgen05_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tmap_a, tmap_w, p);
-    SFB_CHECK_LAUNCH();
+    const int max_pairs = num_sms() / 2;
+    const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2>, tmap_a, tmap_w, p));
     return SFB_OK;
 }

@@ -25,7 +25,7 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(1, id='simple')])
+@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(2, id='tc1cta'), pytest.param(3, id='tcpair'), pytest.param(1, id='simple')])
 @pytest.mark.parametrize('M,N,K', GEMM_SHAPES)
 def test_gemm_bias(cuda_device, impl, M, N, K):
     from synchformer_b200 import ops
@@ -41,7 +41,7 @@ def test_gemm_bias(cuda_device, impl, M, N, K):
     assert (out.float() - ref).abs().max() <= 1e-2 * ref.abs().max() + 1e-3
 
 
-@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(1, id='simple')])
+@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(2, id='tc1cta'), pytest.param(1, id='simple')])
 def test_gemm_epilogues(cuda_device, impl):
     from synchformer_b200 import ops
     g = torch.Generator(device='cuda').manual_seed(3)
@@ -188,8 +188,9 @@ def test_plain_self_attention(cuda_device, impl, L, heads, hd):
     assert (got - ref).abs().max() < 3e-2
 
 
+@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(1, id='simple')])
 @pytest.mark.parametrize('Lk,inner,row_rows', [(196, 8, 1), (12, 6, 6)])
-def test_aggregator_cls_query_attention(cuda_device, Lk, inner, row_rows):
+def test_aggregator_cls_query_attention(cuda_device, Lk, inner, row_rows, impl):
     """One shared CLS query per head against strided K/V groups plus a prefix CLS key/value (motionformer.py:301-334)."""
     from synchformer_b200 import ops
     n, D = 3, 768
@@ -201,7 +202,7 @@ def test_aggregator_cls_query_attention(cuda_device, Lk, inner, row_rows):
     inner_rows = Lk if row_rows == 1 else 1
     ops.attention(cls_qkv, kv, kv[:, D:], out, q_strides=(0, 0, 0), kv_strides=(rows_per_seg * 2 * D, inner_rows * 2 * D, row_rows * 2 * D),
                   o_strides=(inner * D, D, D), n_outer=n, n_inner=inner, n_heads=12, head_dim=64, Lq=1, Lk=Lk, scale=0.125,
-                  k_prefix=cls_qkv[:, D:], v_prefix=cls_qkv[:, 2 * D:], prefix_outer=0)
+                  k_prefix=cls_qkv[:, D:], v_prefix=cls_qkv[:, 2 * D:], prefix_outer=0, impl=impl)
     kvf = kv.float().view(n, rows_per_seg, 2, 12, 64)
     if row_rows == 1:
         grp = kvf.view(n, inner, Lk, 2, 12, 64)
@@ -223,14 +224,18 @@ def test_im2col_video(cuda_device, dtype):
     g = torch.Generator(device='cuda').manual_seed(1)
     if dtype == torch.uint8:
         vis = torch.randint(0, 256, (n, 16, 3, 224, 224), device='cuda', generator=g, dtype=torch.uint8)
-        visf = (vis.float() / 255.0 - 0.5) / 0.5                      # dataset/transforms.py:647-669
+        visf = ((vis.double() / 255.0 - 0.5) / 0.5).float()           # dataset/transforms.py:647-669, exact value rounded once
     else:
         vis = (torch.rand(n, 16, 3, 224, 224, device='cuda', generator=g) * 2 - 1).to(dtype)
         visf = vis.float()
     a = ops.im2col_video(vis)
     ref = visf.view(n, 8, 2, 3, 14, 16, 14, 16).permute(0, 1, 4, 6, 3, 2, 5, 7).reshape(n * 1568, 1536)
     torch.cuda.synchronize()
-    assert torch.equal(a, ref.to(torch.bfloat16))
+    if dtype == torch.uint8:   # the fused normalisation rounds once in fp32: at most 1 bf16 ulp away, and only on rounding ties
+        diff = (a.float() - ref.to(torch.bfloat16).float()).abs()
+        assert float(diff.max()) <= 2.0 ** -8 and float((diff > 0).float().mean()) < 1e-3
+    else:
+        assert torch.equal(a, ref.to(torch.bfloat16))
 
 
 def test_patch_embed_equals_conv3d(cuda_device):
