@@ -211,21 +211,42 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     gemm_flops, gemm_ms, gemm_n = gt.summary()
 
-    # end-to-end: the public call (Synchformer.forward) fed from pinned HOST buffers, logits read back, inside the timed region
-    vis_d, wave_d = torch.empty_like(vis), torch.empty_like(wave)
-    del vis, wave
+    # end-to-end: the public call (Synchformer.forward) fed from pinned HOST buffers, logits read back, all inside the timed region.
+    # Two device input buffers and a copy stream: the H2D copy of step i+1 runs while step i computes (what a prefetching
+    # DataLoader + non_blocking .to() gives the reference harness); every step still pays its own copy and its own read-back.
+    bufs = [(vis, wave), (torch.empty_like(vis), torch.empty_like(wave))]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        vis_d.copy_(vis_h, non_blocking=True)
-        wave_d.copy_(wave_h, non_blocking=True)
-        return step(vis_d, wave_d).float().cpu()
-    e2e_step()
+    def prefetch(b):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            bufs[b][0].copy_(vis_h, non_blocking=True)
+            bufs[b][1].copy_(wave_h, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_run(n):
+        for b in range(2):
+            consumed[b].record()
+        prefetch(0)
+        out = None
+        for i in range(n):
+            b = i & 1
+            if i + 1 < n:
+                prefetch(b ^ 1)
+            torch.cuda.current_stream().wait_event(ready[b])
+            lg = step(*bufs[b])
+            consumed[b].record()
+            out = lg.float().cpu()                               # device -> host read of the step's result
+        return out
+
+    e2e_run(2)
     barrier()
-    e2e_steps = max(2, min(args.steps, 3))
+    e2e_steps = max(3, min(args.steps, 5))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(e2e_steps):
-        out_h = e2e_step()
+    out_h = e2e_run(e2e_steps)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)

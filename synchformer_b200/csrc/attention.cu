@@ -1,13 +1,14 @@
 // K6-K11: softmax attention on strided bf16 Q/K/V views of the fused qkv activations (see sfb_attn_desc).
 //
 // Three kernels behind one entry point:
-//   attn_mma_kernel<HD>    Lq >= 16: one CTA per (outer, inner, head).  Q/K/V rows are staged once in padded shared
-//                          memory with cp.async, each warp owns 16 query rows and walks the keys in chunks of 64 with
+//   attn_mma_kernel<HD>    Lq >= 16: persistent CTAs loop over (outer, inner, head) problems.  Q/K/V rows are staged in padded
+//                          shared memory with cp.async, double-buffered so the next problem streams in while this one is
+//                          computed; each warp owns 16 query rows and walks the keys in chunks of 64 with
 //                          mma.sync.m16n8k16 (bf16 in, fp32 accumulate) for QK^T and PV and a register-resident online
 //                          softmax (quad shuffles only).  Space attention 196x197, AST 74x74, sync 198x198 (hd 96).
-//   attn_time_kernel       Lq = Lk = 8 + CLS prefix, hd 64 (Motionformer time attention): one thread per (query frame,
-//                          head); the 8 lanes that share a (position, head) read the same K/V addresses, so the loads
-//                          broadcast and no shared memory or shuffles are needed.
+//   attn_time_mma_kernel   Lq = Lk = 8 + CLS prefix, hd 64 (Motionformer time attention): two locations per block-diagonal
+//                          m16n8k16 problem, one warp per head, persistent double-buffered cp.async staging.
+//   attn_time_kernel       the same on CUDA cores (one thread per (query frame, head)); kept for odd location counts.
 //   attn_row1_kernel       Lq = 1, hd 64 (Motionformer CLS query 1x1569, aggregator CLS rows 1x197 / 1x13): one CTA per problem,
 //                          8 lanes per key row, 32 private online-softmax states merged through shared memory.
 //   attn_generic_kernel<HD> one warp per query row, lanes split the head dim: the bring-up cross-check for the other three.
@@ -286,160 +287,306 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 template <int HD>
-__global__ void __launch_bounds__(HD == 64 ? 512 : 416) attn_mma_kernel(const Desc d, int Lq_pad, int Lk_pad) {
+__global__ void __launch_bounds__(HD == 64 ? 512 : 416) attn_mma_kernel(const Desc d, int Lq_pad, int Lk_pad, int n_buf, int n_prob) {
     constexpr int PITCH = HD * 2 + 16;      // bytes per smem row; +16 keeps ldmatrix rows on distinct bank groups
     constexpr int CHUNKS = HD / 8;          // 16-byte chunks per row
     constexpr int KSTEPS = HD / 16;         // k16 steps over the head dim
     constexpr int NT_O = HD / 8;            // n8 tiles of the output
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-    const uint32_t sK = sQ + Lq_pad * PITCH;
-    const uint32_t sV = sK + Lk_pad * PITCH;
-
-    int pidx = blockIdx.x;
-    const int h = pidx % d.n_heads;
-    pidx /= d.n_heads;
-    const int i = pidx % d.n_inner;
-    const int o = pidx / d.n_inner;
+    const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const uint32_t buf_bytes = static_cast<uint32_t>(Lq_pad + 2 * Lk_pad) * PITCH;
     const int Lkp = d.Lk + d.has_prefix;
     const int tid = threadIdx.x, nthr = blockDim.x;
-
-    // ---- stage Q, K, V (zero-fill the padding rows so 0 * garbage never produces NaN) ----
-    const __nv_bfloat16 *qg = d.q + o * d.q_outer + i * d.q_inner + h * HD;
-    for (int c = tid; c < Lq_pad * CHUNKS; c += nthr) {
-        const int r = c / CHUNKS, cc = c % CHUNKS;
-        const uint32_t dst = sQ + r * PITCH + cc * 16;
-        if (r < d.Lq)
-            cp_async16(dst, qg + static_cast<int64_t>(r) * d.q_row + cc * 8);
-        else
-            *reinterpret_cast<uint4 *>(smem + (dst - sQ)) = make_uint4(0, 0, 0, 0);
-    }
-    const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD;
-    const int64_t pre_base = o * d.prefix_outer + h * HD;
-    for (int c = tid; c < Lk_pad * CHUNKS; c += nthr) {
-        const int r = c / CHUNKS, cc = c % CHUNKS;
-        const uint32_t dk = sK + r * PITCH + cc * 16, dv = sV + r * PITCH + cc * 16;
-        if (r < Lkp) {
-            const bool pre = d.has_prefix && r == 0;
-            const int64_t off = (pre ? pre_base : kv_base + static_cast<int64_t>(r - d.has_prefix) * d.kv_row) + cc * 8;
-            cp_async16(dk, (pre ? d.kp : d.k) + off);
-            cp_async16(dv, (pre ? d.vp : d.v) + off);
-        } else {
-            *reinterpret_cast<uint4 *>(smem + (dk - sQ)) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4 *>(smem + (dv - sQ)) = make_uint4(0, 0, 0, 0);
-        }
-    }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const int q0 = warp * 16;
-    if (q0 >= Lq_pad) return;
 
-    // Q fragments for this warp's 16 rows (A operand, row-major): lanes 0-15 -> rows, lanes 16-31 -> +8 columns
-    uint32_t qa[KSTEPS][4];
-    {
-        const uint32_t base = sQ + (q0 + (lane & 15)) * PITCH + (lane >> 4) * 16;
-#pragma unroll
-        for (int ks = 0; ks < KSTEPS; ++ks) ldmatrix_x4(base + ks * 32, qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    // K / V padding rows are zeroed once per buffer (0 * garbage must never produce NaN); cp.async only ever writes valid rows.
+    // Q padding rows feed query rows that are never stored, so they need no initialisation.
+    for (int bsel = 0; bsel < n_buf; ++bsel) {
+        uint8_t *bk = smem + bsel * buf_bytes + Lq_pad * PITCH;
+        for (int c = tid; c < (Lk_pad - Lkp) * CHUNKS; c += nthr) {
+            const int r = Lkp + c / CHUNKS, cc = c % CHUNKS;
+            *reinterpret_cast<uint4 *>(bk + r * PITCH + cc * 16) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(bk + (Lk_pad + r) * PITCH + cc * 16) = make_uint4(0, 0, 0, 0);
+        }
     }
-    float oacc[NT_O][4];
-#pragma unroll
-    for (int n = 0; n < NT_O; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g+8
+
+    // issue the cp.async loads of one problem's Q, K, V rows into buffer `bsel` (one commit group)
+    auto issue_loads = [&](int prob, int bsel) {
+        const int h = prob % d.n_heads;
+        const int i = (prob / d.n_heads) % d.n_inner;
+        const int o = prob / (d.n_heads * d.n_inner);
+        const uint32_t sQ = s0 + bsel * buf_bytes, sK = sQ + Lq_pad * PITCH, sV = sK + Lk_pad * PITCH;
+        const __nv_bfloat16 *qg = d.q + o * d.q_outer + i * d.q_inner + h * HD;
+        for (int c = tid; c < d.Lq * CHUNKS; c += nthr) {
+            const int r = c / CHUNKS, cc = c % CHUNKS;
+            cp_async16(sQ + r * PITCH + cc * 16, qg + static_cast<int64_t>(r) * d.q_row + cc * 8);
+        }
+        const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD;
+        const int64_t pre_base = o * d.prefix_outer + h * HD;
+        for (int c = tid; c < Lkp * CHUNKS; c += nthr) {
+            const int r = c / CHUNKS, cc = c % CHUNKS;
+            const bool pre = d.has_prefix && r == 0;
+            const int64_t off = (pre ? pre_base : kv_base + static_cast<int64_t>(r - d.has_prefix) * d.kv_row) + cc * 8;
+            cp_async16(sK + r * PITCH + cc * 16, (pre ? d.kp : d.k) + off);
+            cp_async16(sV + r * PITCH + cc * 16, (pre ? d.vp : d.v) + off);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
     const float sl2 = d.scale * 1.4426950408889634f;            // scores are kept in log2 units
+    int bsel = 0;
+    if (static_cast<int>(blockIdx.x) < n_prob) issue_loads(blockIdx.x, 0);
+    // persistent loop: while the tensor cores work on problem p, cp.async streams problem p + gridDim.x into the other buffer
+    for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                        // buffer `bsel` is complete and visible; the other buffer is free
+        const int next = prob + gridDim.x;
+        if (n_buf == 2 && next < n_prob) issue_loads(next, bsel ^ 1);
 
-    for (int kc = 0; kc < Lk_pad; kc += 64) {
-        const int nkb = min(4, (Lk_pad - kc) >> 4);   // 16-key blocks in this chunk (warp-uniform)
-        float s[8][4];
+        const uint32_t sQ = s0 + bsel * buf_bytes, sK = sQ + Lq_pad * PITCH, sV = sK + Lk_pad * PITCH;
+        // Q fragments for this warp's 16 rows (A operand, row-major): lanes 0-15 -> rows, lanes 16-31 -> +8 columns
+        uint32_t qa[KSTEPS][4];
+        {
+            const uint32_t base = sQ + (q0 + (lane & 15)) * PITCH + (lane >> 4) * 16;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-        // ---- S = Q K^T : per 16-key block two n8 tiles; B fragments straight from the row-major K rows ----
+            for (int ks = 0; ks < KSTEPS; ++ks) ldmatrix_x4(base + ks * 32, qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+        }
+        float oacc[NT_O][4];
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-            if (kb < nkb) {
-                const uint32_t kaddr = sK + (kc + kb * 16 + (lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 16;
+        for (int n = 0; n < NT_O; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g+8
+
+        for (int kc = 0; kc < Lk_pad; kc += 64) {
+            const int nkb = min(4, (Lk_pad - kc) >> 4);   // 16-key blocks in this chunk (warp-uniform)
+            float s[8][4];
 #pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                    uint32_t b0, b1, b2, b3;
-                    ldmatrix_x4(kaddr + ks * 32, b0, b1, b2, b3);
-                    mma_bf16_16816(s[2 * kb], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
-                    mma_bf16_16816(s[2 * kb + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+            for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+            // ---- S = Q K^T : per 16-key block two n8 tiles; B fragments straight from the row-major K rows ----
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+                if (kb < nkb) {
+                    const uint32_t kaddr = sK + (kc + kb * 16 + (lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 16;
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                        uint32_t b0, b1, b2, b3;
+                        ldmatrix_x4(kaddr + ks * 32, b0, b1, b2, b3);
+                        mma_bf16_16816(s[2 * kb], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+                        mma_bf16_16816(s[2 * kb + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+                    }
+                }
+            }
+            // ---- scale, mask the padded keys, online softmax ----
+            float mx0 = m0, mx1 = m1;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const int key = kc + n * 8 + t4 * 2;
+                const bool live = n < 2 * nkb;
+                s[n][0] = (live && key < Lkp) ? s[n][0] * sl2 : -INFINITY;
+                s[n][1] = (live && key + 1 < Lkp) ? s[n][1] * sl2 : -INFINITY;
+                s[n][2] = (live && key < Lkp) ? s[n][2] * sl2 : -INFINITY;
+                s[n][3] = (live && key + 1 < Lkp) ? s[n][3] * sl2 : -INFINITY;
+                mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float c0 = fast_exp2(m0 - mx0), c1 = fast_exp2(m1 - mx1);   // first chunk: exp2(-inf) = 0
+            m0 = mx0, m1 = mx1;
+            float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                s[n][0] = fast_exp2(s[n][0] - mx0), s[n][1] = fast_exp2(s[n][1] - mx0);
+                s[n][2] = fast_exp2(s[n][2] - mx1), s[n][3] = fast_exp2(s[n][3] - mx1);
+                ps0 += s[n][0] + s[n][1];
+                ps1 += s[n][2] + s[n][3];
+            }
+            l0 = l0 * c0 + ps0;   // per-thread partial sums; reduced over the quad at the end
+            l1 = l1 * c1 + ps1;
+#pragma unroll
+            for (int n = 0; n < NT_O; ++n) oacc[n][0] *= c0, oacc[n][1] *= c0, oacc[n][2] *= c1, oacc[n][3] *= c1;
+            // ---- O += P V : P from the S accumulators (C layout == A layout), V^T fragments via ldmatrix.trans ----
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+                if (kb < nkb) {
+                    const uint32_t a0 = pack_bf16x2(s[2 * kb][0], s[2 * kb][1]);
+                    const uint32_t a1 = pack_bf16x2(s[2 * kb][2], s[2 * kb][3]);
+                    const uint32_t a2 = pack_bf16x2(s[2 * kb + 1][0], s[2 * kb + 1][1]);
+                    const uint32_t a3 = pack_bf16x2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
+                    const uint32_t vaddr = sV + (kc + kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16;
+#pragma unroll
+                    for (int n2 = 0; n2 < NT_O / 2; ++n2) {
+                        uint32_t b0, b1, b2, b3;
+                        ldmatrix_x4_trans(vaddr + n2 * 32, b0, b1, b2, b3);
+                        mma_bf16_16816(oacc[2 * n2], a0, a1, a2, a3, b0, b1);
+                        mma_bf16_16816(oacc[2 * n2 + 1], a0, a1, a2, a3, b2, b3);
+                    }
                 }
             }
         }
-        // ---- scale, mask the padded keys, online softmax ----
-        float mx0 = m0, mx1 = m1;
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+
+        // ---- stage the 16 x HD output tile in this warp's (now dead) Q rows, then store 16 B per lane ----
+        __syncwarp();
+        uint8_t *so = smem + bsel * buf_bytes + q0 * PITCH;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            const int key = kc + n * 8 + t4 * 2;
-            const bool live = n < 2 * nkb;
-            s[n][0] = (live && key < Lkp) ? s[n][0] * sl2 : -INFINITY;
-            s[n][1] = (live && key + 1 < Lkp) ? s[n][1] * sl2 : -INFINITY;
-            s[n][2] = (live && key < Lkp) ? s[n][2] * sl2 : -INFINITY;
-            s[n][3] = (live && key + 1 < Lkp) ? s[n][3] * sl2 : -INFINITY;
-            mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+        for (int n = 0; n < NT_O; ++n) {
+            *reinterpret_cast<uint32_t *>(so + g * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][0] * i0, oacc[n][1] * i0);
+            *reinterpret_cast<uint32_t *>(so + (g + 8) * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][2] * i1, oacc[n][3] * i1);
         }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float c0 = fast_exp2(m0 - mx0), c1 = fast_exp2(m1 - mx1);   // first chunk: exp2(-inf) = 0
-        m0 = mx0, m1 = mx1;
-        float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            s[n][0] = fast_exp2(s[n][0] - mx0), s[n][1] = fast_exp2(s[n][1] - mx0);
-            s[n][2] = fast_exp2(s[n][2] - mx1), s[n][3] = fast_exp2(s[n][3] - mx1);
-            ps0 += s[n][0] + s[n][1];
-            ps1 += s[n][2] + s[n][3];
-        }
-        l0 = l0 * c0 + ps0;   // per-thread partial sums; reduced over the quad at the end
-        l1 = l1 * c1 + ps1;
-#pragma unroll
-        for (int n = 0; n < NT_O; ++n) oacc[n][0] *= c0, oacc[n][1] *= c0, oacc[n][2] *= c1, oacc[n][3] *= c1;
-        // ---- O += P V : P from the S accumulators (C layout == A layout), V^T fragments via ldmatrix.trans ----
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-            if (kb < nkb) {
-                const uint32_t a0 = pack_bf16x2(s[2 * kb][0], s[2 * kb][1]);
-                const uint32_t a1 = pack_bf16x2(s[2 * kb][2], s[2 * kb][3]);
-                const uint32_t a2 = pack_bf16x2(s[2 * kb + 1][0], s[2 * kb + 1][1]);
-                const uint32_t a3 = pack_bf16x2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
-                const uint32_t vaddr = sV + (kc + kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16;
-#pragma unroll
-                for (int n2 = 0; n2 < NT_O / 2; ++n2) {
-                    uint32_t b0, b1, b2, b3;
-                    ldmatrix_x4_trans(vaddr + n2 * 32, b0, b1, b2, b3);
-                    mma_bf16_16816(oacc[2 * n2], a0, a1, a2, a3, b0, b1);
-                    mma_bf16_16816(oacc[2 * n2 + 1], a0, a1, a2, a3, b2, b3);
-                }
+        __syncwarp();
+        {
+            const int h = prob % d.n_heads;
+            const int i = (prob / d.n_heads) % d.n_inner;
+            const int o = prob / (d.n_heads * d.n_inner);
+            __nv_bfloat16 *og = d.out + o * d.o_outer + i * d.o_inner + h * HD;
+            for (int c = lane; c < 16 * CHUNKS; c += 32) {
+                const int r = c / CHUNKS, cc = c % CHUNKS;
+                if (q0 + r < d.Lq)
+                    *reinterpret_cast<uint4 *>(og + static_cast<int64_t>(q0 + r) * d.o_row + cc * 8) = *reinterpret_cast<const uint4 *>(so + r * PITCH + cc * 16);
             }
         }
+        if (n_buf == 2) {
+            bsel ^= 1;
+        } else {
+            __syncthreads();                                    // single buffer: everybody is done before it is refilled
+            if (next < n_prob) issue_loads(next, 0);
+        }
     }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
-    // ---- stage the 16 x HD output tile in this warp's (now dead) Q rows, then store 16 B per lane ----
-    __syncwarp();
-    uint8_t *so = smem + q0 * PITCH;
+// --------------------------------------------------------------- Motionformer time attention on tensor cores
+// Lq = Lk = 8 frames + CLS prefix key, hd 64.  A persistent CTA handles one PAIR of spatial locations for all heads per
+// iteration (one warp per head): the 16 x (3 * n_heads * 64) tile [2 locations x 8 frames] x [q | k | v] is staged with cp.async
+// (double-buffered, fully coalesced 1.5 KB row pieces), and the two 8 x 9 attentions of a pair are evaluated as ONE block-
+// diagonal m16n8k16 problem: S = [Q_a; Q_b] [K_a | K_b | k_cls]^T keeps the two diagonal 8 x 8 blocks and the CLS column,
+// O = P V with P zero off the diagonal blocks.  28 mma.sync per (pair, head) instead of 2 x 9 x 64 x 2 x 8 CUDA-core FMAs.
+__global__ void __launch_bounds__(512) attn_time_mma_kernel(const Desc d, int n_pairs_total) {
+    constexpr int HD = 64;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int H = d.n_heads;
+    const int seg_bytes = H * HD * 2;                 // one of q / k / v for one token, all heads
+    const int PITCH = 3 * seg_bytes + 16;             // +16: ldmatrix rows land on distinct bank groups
+    const int cls_off = 16 * PITCH;                   // [k_cls | v_cls] of the segment
+    const uint32_t buf_bytes = static_cast<uint32_t>(cls_off + 2 * seg_bytes + 16);
+    const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;       // warp == head
+    const int g = lane >> 2, t4 = lane & 3;
+    const int pairs_per_outer = d.n_inner / 2;
+    const int chunks_seg = seg_bytes / 16;
+
+    auto issue_loads = [&](int pair, int bsel) {
+        const int o = pair / pairs_per_outer;
+        const int i0 = (pair % pairs_per_outer) * 2;
+        const uint32_t sb = s0 + bsel * buf_bytes;
+        for (int c = tid; c < 16 * 3 * chunks_seg; c += nthr) {
+            const int cc = c % chunks_seg;
+            const int part = (c / chunks_seg) % 3;    // 0 q, 1 k, 2 v
+            const int r = c / (3 * chunks_seg);       // 0..15 = location (r >> 3), frame (r & 7)
+            const int64_t tok = static_cast<int64_t>(i0 + (r >> 3));
+            const __nv_bfloat16 *src = part == 0 ? d.q + o * d.q_outer + tok * d.q_inner + static_cast<int64_t>(r & 7) * d.q_row
+                                                 : (part == 1 ? d.k : d.v) + o * d.kv_outer + tok * d.kv_inner + static_cast<int64_t>(r & 7) * d.kv_row;
+            cp_async16(sb + r * PITCH + part * seg_bytes + cc * 16, src + cc * 8);
+        }
+        for (int c = tid; c < 2 * chunks_seg; c += nthr) {
+            const int cc = c % chunks_seg, part = c / chunks_seg;
+            cp_async16(sb + cls_off + part * seg_bytes + cc * 16, (part == 0 ? d.kp : d.vp) + o * d.prefix_outer + cc * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const float sl2 = d.scale * 1.4426950408889634f;
+    int bsel = 0;
+    if (static_cast<int>(blockIdx.x) < n_pairs_total) issue_loads(blockIdx.x, 0);
+    for (int pair = blockIdx.x; pair < n_pairs_total; pair += gridDim.x) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const int next = pair + gridDim.x;
+        if (next < n_pairs_total) issue_loads(next, bsel ^ 1);
+
+        if (warp < H) {
+            const uint32_t sb = s0 + bsel * buf_bytes;
+            const uint32_t hq = sb + warp * (HD * 2), hk = hq + seg_bytes, hv = hk + seg_bytes;
+            const uint32_t ck = sb + cls_off + warp * (HD * 2), cv = ck + seg_bytes;
+            float s[3][4];
 #pragma unroll
-    for (int n = 0; n < NT_O; ++n) {
-        *reinterpret_cast<uint32_t *>(so + g * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][0] * i0, oacc[n][1] * i0);
-        *reinterpret_cast<uint32_t *>(so + (g + 8) * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][2] * i1, oacc[n][3] * i1);
+            for (int n = 0; n < 3; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t a0, a1, a2, a3, b0, b1, b2, b3, c0, c1;
+                ldmatrix_x4(hq + (lane & 15) * PITCH + (lane >> 4) * 16 + ks * 32, a0, a1, a2, a3);
+                ldmatrix_x4(hk + ((lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 16 + ks * 32, b0, b1, b2, b3);
+                // CLS key: every row address of the 8 x 8 matrices points at the single k_cls row (columns 1..7 are duplicates, ignored)
+                asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(c0), "=r"(c1) : "r"(ck + ((lane >> 3) & 1) * 16 + ks * 32));
+                mma_bf16_16816(s[0], a0, a1, a2, a3, b0, b1);     // x keys of location a: rows 0-7 valid
+                mma_bf16_16816(s[1], a0, a1, a2, a3, b2, b3);     // x keys of location b: rows 8-15 valid
+                mma_bf16_16816(s[2], a0, a1, a2, a3, c0, c1);     // x CLS key: column 0 valid
+            }
+            // row g belongs to location a (scores s[0][0..1] over the quad), row g+8 to location b (s[1][2..3]); CLS score from lane t4 == 0
+            const float cls0 = __shfl_sync(0xffffffffu, s[2][0], lane & ~3) * sl2;
+            const float cls1 = __shfl_sync(0xffffffffu, s[2][2], lane & ~3) * sl2;
+            float x0 = s[0][0] * sl2, x1 = s[0][1] * sl2, y0 = s[1][2] * sl2, y1 = s[1][3] * sl2;
+            float mx0 = fmaxf(fmaxf(x0, x1), cls0), mx1 = fmaxf(fmaxf(y0, y1), cls1);
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            x0 = fast_exp2(x0 - mx0), x1 = fast_exp2(x1 - mx0), y0 = fast_exp2(y0 - mx1), y1 = fast_exp2(y1 - mx1);
+            const float pc0 = fast_exp2(cls0 - mx0), pc1 = fast_exp2(cls1 - mx1);
+            float l0 = x0 + x1, l1 = y0 + y1;
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            const float i0 = 1.0f / (l0 + pc0), i1 = 1.0f / (l1 + pc1);
+            // P (block diagonal) as the A operand of two k16 steps: [keys a | keys b] and [CLS, 15 zeros]
+            const uint32_t pa0 = pack_bf16x2(x0 * i0, x1 * i0), pa3 = pack_bf16x2(y0 * i1, y1 * i1);
+            const uint32_t pb0 = t4 == 0 ? pack_bf16x2(pc0 * i0, 0.f) : 0u, pb1 = t4 == 0 ? pack_bf16x2(pc1 * i1, 0.f) : 0u;
+            float oacc[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
+#pragma unroll
+            for (int n2 = 0; n2 < 4; ++n2) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(hv + ((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16 + n2 * 32, b0, b1, b2, b3);
+                mma_bf16_16816(oacc[2 * n2], pa0, 0u, 0u, pa3, b0, b1);
+                mma_bf16_16816(oacc[2 * n2 + 1], pa0, 0u, 0u, pa3, b2, b3);
+                // CLS value: all 16 "key" rows of this k16 step point at v_cls (finite), only key 0 has a non-zero probability
+                ldmatrix_x4_trans(cv + (lane >> 4) * 16 + n2 * 32, b0, b1, b2, b3);
+                mma_bf16_16816(oacc[2 * n2], pb0, pb1, 0u, 0u, b0, b1);
+                mma_bf16_16816(oacc[2 * n2 + 1], pb0, pb1, 0u, 0u, b2, b3);
+            }
+            // stage the 16 x 64 output in this head's (dead) Q columns, then 16-byte coalesced stores
+            __syncwarp();
+            uint8_t *so = smem + bsel * buf_bytes + warp * (HD * 2);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                *reinterpret_cast<uint32_t *>(so + g * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][0], oacc[n][1]);
+                *reinterpret_cast<uint32_t *>(so + (g + 8) * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][2], oacc[n][3]);
+            }
+            __syncwarp();
+            const int o = pair / pairs_per_outer;
+            const int i0p = (pair % pairs_per_outer) * 2;
+            __nv_bfloat16 *og = d.out + o * d.o_outer + warp * HD;
+#pragma unroll
+            for (int c = lane; c < 16 * 8; c += 32) {
+                const int r = c >> 3, cc = c & 7;
+                *reinterpret_cast<uint4 *>(og + static_cast<int64_t>(i0p + (r >> 3)) * d.o_inner + static_cast<int64_t>(r & 7) * d.o_row + cc * 8) =
+                    *reinterpret_cast<const uint4 *>(so + r * PITCH + cc * 16);
+            }
+        }
+        bsel ^= 1;
     }
-    __syncwarp();
-    __nv_bfloat16 *og = d.out + o * d.o_outer + i * d.o_inner + h * HD;
-    for (int c = lane; c < 16 * CHUNKS; c += 32) {
-        const int r = c / CHUNKS, cc = c % CHUNKS;
-        if (q0 + r < d.Lq)
-            *reinterpret_cast<uint4 *>(og + static_cast<int64_t>(q0 + r) * d.o_row + cc * 8) = *reinterpret_cast<const uint4 *>(so + r * PITCH + cc * 16);
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace attn
@@ -482,21 +629,32 @@ extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
     if (desc->impl == 0 && aligned16 && d.Lq >= 16 && Lq_pad <= (HD == 64 ? 256 : 208) && mma_smem <= 200 * 1024) {
         const int threads = (Lq_pad / 16) * 32;
         SFB_CHECK_ARG(n_prob < (1ll << 31), "sfb_attention: too many problems");
+        // two staging buffers (load of the next problem overlaps the math of this one) whenever they fit
+        const int n_buf = 2 * mma_smem <= 220 * 1024 ? 2 : 1;
+        const int smem_bytes = static_cast<int>(mma_smem) * n_buf;
+        int occ = 1;
         if (HD == 64) {
-            static int64_t cur = 0;
-            if (mma_smem > cur) {
-                SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(mma_smem)));
-                cur = mma_smem;
+            static int cur = 0;
+            if (smem_bytes > cur) {
+                SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+                cur = smem_bytes;
             }
-            attn_mma_kernel<64><<<static_cast<unsigned>(n_prob), threads, mma_smem, st>>>(d, Lq_pad, Lk_pad);
+            SFB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attn_mma_kernel<64>, threads, smem_bytes));
         } else {
-            static int64_t cur = 0;
-            if (mma_smem > cur) {
-                SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(mma_smem)));
-                cur = mma_smem;
+            static int cur = 0;
+            if (smem_bytes > cur) {
+                SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+                cur = smem_bytes;
             }
-            attn_mma_kernel<96><<<static_cast<unsigned>(n_prob), threads, mma_smem, st>>>(d, Lq_pad, Lk_pad);
+            SFB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attn_mma_kernel<96>, threads, smem_bytes));
         }
+        if (occ < 1) occ = 1;
+        const int64_t max_ctas = static_cast<int64_t>(num_sms()) * occ;
+        const unsigned grid = static_cast<unsigned>(n_prob < max_ctas ? n_prob : max_ctas);
+        if (HD == 64)
+            attn_mma_kernel<64><<<grid, threads, smem_bytes, st>>>(d, Lq_pad, Lk_pad, n_buf, static_cast<int>(n_prob));
+        else
+            attn_mma_kernel<96><<<grid, threads, smem_bytes, st>>>(d, Lq_pad, Lk_pad, n_buf, static_cast<int>(n_prob));
         SFB_CHECK_LAUNCH();
         return SFB_OK;
     }
@@ -505,6 +663,23 @@ extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
         attn_row1_kernel<<<static_cast<unsigned>(n_prob), 256, 0, st>>>(d);
         SFB_CHECK_LAUNCH();
         return SFB_OK;
+    }
+    if (desc->impl == 0 && aligned16 && HD == 64 && d.Lq == 8 && d.Lk == 8 && d.has_prefix && d.n_inner % 2 == 0 && d.n_heads <= 16) {
+        const int seg_bytes = d.n_heads * 64 * 2;
+        const int smem_bytes = 2 * (16 * (3 * seg_bytes + 16) + 2 * seg_bytes + 16);
+        if (smem_bytes <= 220 * 1024) {
+            static int cur = 0;
+            if (smem_bytes > cur) {
+                SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_time_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+                cur = smem_bytes;
+            }
+            const int64_t n_pairs = static_cast<int64_t>(d.n_outer) * (d.n_inner / 2);
+            SFB_CHECK_ARG(n_pairs < (1ll << 31), "sfb_attention: too many problems");
+            const unsigned grid = static_cast<unsigned>(n_pairs < num_sms() ? n_pairs : num_sms());
+            attn_time_mma_kernel<<<grid, 32 * d.n_heads, smem_bytes, st>>>(d, static_cast<int>(n_pairs));
+            SFB_CHECK_LAUNCH();
+            return SFB_OK;
+        }
     }
     if (desc->impl == 0 && aligned16 && HD == 64 && d.Lq == 8 && d.Lk == 8 && d.has_prefix && d.n_heads % 4 == 0) {
         const int64_t warps = static_cast<int64_t>(d.n_outer) * d.n_inner * (d.n_heads / 4);
