@@ -1,6 +1,6 @@
 // K6-K11: softmax attention on strided bf16 Q/K/V views of the fused qkv activations (see sfb_attn_desc).
 //
-// Three kernels behind one entry point:
+// Kernels behind one entry point (plus attn_space_tc_kernel in attention_tc.cu: tcgen05 / TMEM, used for the 196 x 197 space attention):
 //   attn_mma_kernel<HD>    Lq >= 16: persistent CTAs loop over (outer, inner, head) problems.  Q/K/V rows are staged in padded
 //                          shared memory with cp.async, double-buffered so the next problem streams in while this one is
 //                          computed; each warp owns 16 query rows and walks the keys in chunks of 64 with
@@ -15,22 +15,14 @@
 // All keep scores and statistics in fp32; nothing is materialised in HBM (the reference materialises the attention
 // matrix and ~20 rearrange/cat copies per block: vit_helper.py:34-42,106-153; modeling_ast.py:156-176;
 // modules/transformer.py:67-70).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "attention.cuh"
 
 namespace sfb {
 namespace attn {
 
-struct Desc {
-    const __nv_bfloat16 *q, *k, *v, *kp, *vp;
-    __nv_bfloat16 *out;
-    int64_t q_outer, q_inner, q_row;
-    int64_t kv_outer, kv_inner, kv_row;
-    int64_t o_outer, o_inner, o_row;
-    int64_t prefix_outer;
-    int has_prefix;
-    int n_outer, n_inner, n_heads, Lq, Lk;
-    float scale;
-};
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float *f) {
     f[0] = __uint_as_float(u.x << 16), f[1] = __uint_as_float(u.x & 0xffff0000u);
@@ -626,6 +618,8 @@ extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
     const int64_t mma_smem = static_cast<int64_t>(Lq_pad + 2 * Lk_pad) * (HD * 2 + 16);
     const int64_t n_prob = static_cast<int64_t>(d.n_outer) * d.n_inner * d.n_heads;
 
+    static const bool tc_enabled = !(getenv("SFB_ATTN_TC") && atoi(getenv("SFB_ATTN_TC")) == 0);   // A/B switch for measurements
+    if (desc->impl == 0 && aligned16 && HD == 64 && tc_enabled && tc_supported(d)) return launch_tc(d, st);
     if (desc->impl == 0 && aligned16 && d.Lq >= 16 && Lq_pad <= (HD == 64 ? 256 : 208) && mma_smem <= 200 * 1024) {
         const int threads = (Lq_pad / 16) * 32;
         SFB_CHECK_ARG(n_prob < (1ll << 31), "sfb_attention: too many problems");

@@ -34,6 +34,7 @@ void set_error(const char *fmt, ...);
 #define SFB_CHECK_LAUNCH() SFB_CHECK_CUDA(cudaGetLastError())
 
 int num_sms();
+int encode_tmap_bf16_2d(void *map, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 

@@ -1,0 +1,16 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+O=gpurun_out
+rm -f $O/summary.txt
+python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
+PT="python -m pytest -q -m gpu -p no:cacheprovider -x --timeout 60 --timeout-method thread"
+timeout 100 $PT tests/test_kernels_gpu.py -k "divided" > $O/pytest_attn.log 2>&1; echo "attn tests rc=$?" >> $O/summary.txt
+timeout 150 $PT tests/test_kernels_gpu.py > $O/pytest_kernels.log 2>&1; echo "kernels rc=$?" >> $O/summary.txt
+timeout 150 $PT tests/test_model_gpu.py -s > $O/pytest_model.log 2>&1; echo "model rc=$?" >> $O/summary.txt
+timeout 120 python tools/microbench.py > $O/microbench.log 2>&1; echo "microbench rc=$?" >> $O/summary.txt
+timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/bench.log 2>&1; echo "bench rc=$?" >> $O/summary.txt
+cat $O/summary.txt
+tail -15 $O/pytest_attn.log | grep -E "^E|passed|failed|Error" | head; tail -3 $O/pytest_kernels.log; grep -E "parity|passed|failed" $O/pytest_model.log | tail -3
+grep -E "^attn|^layer" $O/microbench.log
+tail -1 $O/bench.log | cut -c1-250
