@@ -1,19 +1,25 @@
 // K7 on the 5th-generation tensor cores: Motionformer space attention (196 queries x 197 keys, hd 64; vit_helper.py:100-158 with
 // einops_to '(b f) n d') as tcgen05.mma with S, P and O resident in TMEM.
 //
-// One persistent CTA per SM (416 threads) loops over (segment, frame, head) problems:
-//   warps 9-12  producers   cp.async 16-byte gathers of the Q / K / V rows (CLS prefix key first) into a 2-stage shared-memory
-//                           ring, written directly in the 128B-swizzled K-major layout the UMMA descriptors expect;
-//                           cp.async.wait_group + fence.proxy.async + mbarrier arrive publishes a stage
+// One persistent CTA per SM (384 threads) loops over (segment, frame, head) problems:
+//   warps 9-11  producers   a 2-stage shared-memory ring of [Q | K | V] tiles in the 128B-swizzled K-major layout the UMMA descriptors
+//                           expect.  When the row strides are regular (they are for the fused qkv activations) ONE thread issues
+//                           three TMA box loads (cp.async.bulk.tensor, 196 x 64 each) per problem and a second warp gathers the
+//                           single CLS key / value row with cp.async; otherwise three warps gather everything with cp.async.
+//                           The CLS prefix row is stored LAST (key order is irrelevant to softmax), so the TMA boxes start on
+//                           swizzle-atom boundaries
 //   warp 8      MMA issuer  S_t = Q_t K^T   (2 row tiles t of 128 queries; 4 x tcgen05.mma M128 N208 K16, operands from smem)
 //                           O_t = P_t V     (13 x tcgen05.mma M128 N64 K16, A = P_t read from TMEM, B = V as an MN-major operand:
 //                           the [key][64 dims] rows are used as they are, no transpose)
-//   warps 0-7   softmax     thread = query row (TMEM lane).  Two passes over the fp32 scores with tcgen05.ld (row max, then
-//                           exp2 / row sum), P written back over S as packed bf16 with tcgen05.st, then the O epilogue:
+//   warps 0-7   softmax     thread = query row (TMEM lane).  Two passes over the fp32 scores with software-pipelined tcgen05.ld
+//                           (row max, then exp2 / row sum), P written back over S as packed bf16 with tcgen05.st, then the O epilogue:
 //                           tcgen05.ld, 1/sum, bf16, one 128-byte row store per thread.
 // TMEM (512 columns): tile t owns columns [256t, 256t+208): S fp32 there; P (bf16 pairs) re-uses columns [0,104) of the same
 // range as the softmax consumes S; O accumulates in columns [128,192) once S is dead.
 // Nothing touches HBM between the qkv activations and the attention output.
+#include <stdlib.h>
+#include <string.h>
+
 #include "attention.cuh"
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -26,8 +32,8 @@ using namespace sfb::tc;
 namespace {
 
 constexpr int HD = 64;
-constexpr int kSoftmaxWarps = 8, kProducerWarps = 4;
-constexpr int kThreadsTc = (kSoftmaxWarps + 1 + kProducerWarps) * 32;   // 416
+constexpr int kSoftmaxWarps = 8, kProducerWarps = 3;   // 12 warps: 170 registers per thread are available
+constexpr int kThreadsTc = (kSoftmaxWarps + 1 + kProducerWarps) * 32;   // 384
 constexpr uint32_t Q_BYTES = 256 * 128;                                 // two 128-row tiles, 128 B per row
 constexpr uint32_t KV_ROWS = 208;                                       // keys padded to a multiple of 16
 constexpr uint32_t KV_BYTES = KV_ROWS * 128;                            // 26 KB, a multiple of 1024
@@ -44,7 +50,26 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(kThreadsTc, 1) attn_space_tc_kernel(const Desc d, int n_prob) {
+__device__ __forceinline__ void softmax_max32(const uint32_t (&r)[32], float &mx) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+}
+// 32 scores -> 16 packed bf16 probability pairs, running sum
+__device__ __forceinline__ void softmax_exp32(const uint32_t (&r)[32], uint32_t (&pk)[16], float sl2, float mxs, float &sum) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const float p0 = ex2f(fmaf(__uint_as_float(r[j]), sl2, -mxs));
+        const float p1 = ex2f(fmaf(__uint_as_float(r[j + 1]), sl2, -mxs));
+        s0 += p0, s1 += p1;
+        pk[j >> 1] = pack_bf16x2(p0, p1);
+    }
+    sum += s0 + s1;
+}
+
+__global__ void __launch_bounds__(kThreadsTc, 1)
+attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                     const Desc d, int n_prob, int use_tma, int q_rows_outer, int q_rows_inner, int kv_rows_outer, int kv_rows_inner) {
     extern __shared__ uint8_t smem_raw[];
     // barriers: full[2] empty[2] | s_ready[2] p_ready[2] o_ready[2] tmem_free[2]
     __shared__ __align__(8) uint64_t bars[12];
@@ -59,14 +84,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attn_space_tc_kernel(const Desc
     auto p_bar = [&](int t) { return bar0 + 8u * (6 + t); };
     auto o_bar = [&](int t) { return bar0 + 8u * (8 + t); };
     auto free_bar = [&](int t) { return bar0 + 8u * (10 + t); };
-    const int Lkp = d.Lk + d.has_prefix;            // <= 208
+    const int Lkp = d.Lk + d.has_prefix;            // <= 208; key row d.Lk is the prefix (CLS) row
     const int n_tiles = (d.Lq + 127) / 128;         // 2 for the space attention
 
-    // zero the staging buffers once: rows that cp.async never writes (key padding, query padding) must hold finite values
+    // zero the staging buffers once: rows that are never written (key padding, query padding) must hold finite values
     for (uint32_t i = threadIdx.x; i < 2 * STAGE_BYTES_TC / 16; i += kThreadsTc) reinterpret_cast<uint4 *>(base_g)[i] = make_uint4(0, 0, 0, 0);
     if (warp == 8 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(full_bar(s), kProducerWarps);
+            mbar_init(full_bar(s), use_tma ? 2 : kProducerWarps);   // TMA: expect_tx arrive + the CLS-row warp; else 3 gather warps
             mbar_init(empty_bar(s), 1);
         }
         for (int t = 0; t < 2; ++t) {
@@ -81,7 +106,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attn_space_tc_kernel(const Desc
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    fence_proxy_async_smem();      // the zero fill must be visible to the tensor cores (async proxy) too
+    if (warp == 9 && lane == 0 && use_tma) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_k);
+        tma_prefetch_desc(&tm_v);
+    }
+    fence_proxy_async_smem();      // the zero fill must be visible to the tensor cores / TMA (async proxy) too
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -89,34 +119,60 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attn_space_tc_kernel(const Desc
 
     if (warp >= 9) {
         // ================================ producers ===================================
-        const int ptid = threadIdx.x - 9 * 32;          // 0..127
-        int it = 0;
-        for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
-            const int s = it & 1;
-            mbar_wait(empty_bar(s), ((it >> 1) & 1) ^ 1u);
-            const int h = prob % d.n_heads;
-            const int i = (prob / d.n_heads) % d.n_inner;
-            const int o = prob / (d.n_heads * d.n_inner);
-            const uint32_t sQ = base + s * STAGE_BYTES_TC, sK = sQ + Q_BYTES, sV = sK + KV_BYTES;
-            const __nv_bfloat16 *qg = d.q + o * d.q_outer + i * d.q_inner + h * HD;
-            for (int c = ptid; c < d.Lq * 8; c += 128) {
-                const int r = c >> 3, cc = c & 7;
-                cp_async16(sQ + r * 128 + ((cc ^ (r & 7)) << 4), qg + static_cast<int64_t>(r) * d.q_row + cc * 8);
+        const int pw = warp - 9;                        // 0..2
+        if (use_tma && pw >= 2) {
+            // idle
+        } else {
+            int it = 0;
+            for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
+                const int s = it & 1;
+                mbar_wait(empty_bar(s), ((it >> 1) & 1) ^ 1u);
+                const int h = prob % d.n_heads;
+                const int i = (prob / d.n_heads) % d.n_inner;
+                const int o = prob / (d.n_heads * d.n_inner);
+                const uint32_t sQ = base + s * STAGE_BYTES_TC, sK = sQ + Q_BYTES, sV = sK + KV_BYTES;
+                const int64_t pre_base = o * d.prefix_outer + h * HD;
+                if (use_tma) {
+                    if (pw == 0) {
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(full_bar(s), static_cast<uint32_t>(d.Lq + 2 * d.Lk) * 128u);
+                            tma_load_2d(sQ, &tm_q, full_bar(s), h * HD, o * q_rows_outer + i * q_rows_inner);
+                            tma_load_2d(sK, &tm_k, full_bar(s), h * HD, o * kv_rows_outer + i * kv_rows_inner);
+                            tma_load_2d(sV, &tm_v, full_bar(s), h * HD, o * kv_rows_outer + i * kv_rows_inner);
+                        }
+                    } else {   // pw == 1: the CLS key / value row -> row d.Lk of the K / V tiles
+                        if (d.has_prefix && lane < 16) {
+                            const int cc = lane & 7, r = d.Lk;
+                            const uint32_t sw = r * 128 + ((cc ^ (r & 7)) << 4);
+                            cp_async16((lane < 8 ? sK : sV) + sw, (lane < 8 ? d.kp : d.vp) + pre_base + cc * 8);
+                        }
+                        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_bar(s));
+                    }
+                } else {
+                    const int ptid = threadIdx.x - 9 * 32;          // 0..95
+                    const __nv_bfloat16 *qg = d.q + o * d.q_outer + i * d.q_inner + h * HD;
+                    for (int c = ptid; c < d.Lq * 8; c += kProducerWarps * 32) {
+                        const int r = c >> 3, cc = c & 7;
+                        cp_async16(sQ + r * 128 + ((cc ^ (r & 7)) << 4), qg + static_cast<int64_t>(r) * d.q_row + cc * 8);
+                    }
+                    const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD;
+                    for (int c = ptid; c < Lkp * 8; c += kProducerWarps * 32) {
+                        const int r = c >> 3, cc = c & 7;
+                        const bool pre = r == d.Lk;                 // only reached when has_prefix
+                        const int64_t off = (pre ? pre_base : kv_base + static_cast<int64_t>(r) * d.kv_row) + cc * 8;
+                        const uint32_t sw = r * 128 + ((cc ^ (r & 7)) << 4);
+                        cp_async16(sK + sw, (pre ? d.kp : d.k) + off);
+                        cp_async16(sV + sw, (pre ? d.vp : d.v) + off);
+                    }
+                    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                    fence_proxy_async_smem();               // generic-proxy writes -> visible to tcgen05.mma (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar(s));
+                }
             }
-            const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD;
-            const int64_t pre_base = o * d.prefix_outer + h * HD;
-            for (int c = ptid; c < Lkp * 8; c += 128) {
-                const int r = c >> 3, cc = c & 7;
-                const bool pre = d.has_prefix && r == 0;
-                const int64_t off = (pre ? pre_base : kv_base + static_cast<int64_t>(r - d.has_prefix) * d.kv_row) + cc * 8;
-                const uint32_t sw = r * 128 + ((cc ^ (r & 7)) << 4);
-                cp_async16(sK + sw, (pre ? d.kp : d.k) + off);
-                cp_async16(sV + sw, (pre ? d.vp : d.v) + off);
-            }
-            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-            fence_proxy_async_smem();               // generic-proxy writes -> visible to tcgen05.mma (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));
         }
     } else if (warp == 8) {
         // ================================ MMA issuer ==================================
@@ -157,55 +213,103 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attn_space_tc_kernel(const Desc
         const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + t * TILE_COLS;
         const float sl2 = d.scale * 1.4426950408889634f;
         const bool tile_live = t < n_tiles;
+        const bool rows_live = t * 128 + (warp & 3) * 32 < d.Lq;    // warp-uniform: a warp whose 32 rows are all padding only keeps the barriers in step
         int it = 0;
         for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
             if (!tile_live) continue;
             mbar_wait(s_bar(t), it & 1);
             tc_fence_after();
-            // pass 1: row maximum over the live keys
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < static_cast<int>(KV_ROWS) / 16; ++c) {
-                uint32_t r[16];
-                tmem_ld16(trow + c * 16, r);
-                tmem_ld_wait();
+            float inv = 0.f;
+            if (rows_live) {
+                uint32_t ra[32], rb[32];
+                // ---- pass 1: row maximum.  Columns 0..191 in six x32 loads (next load in flight while this one is reduced), then 192..207
+                float mx = -INFINITY;
+                tmem_ld32(trow, ra);
+                tmem_ld_wait_dep(ra);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c * 16 + j < Lkp) mx = fmaxf(mx, __uint_as_float(r[j]));
-            }
-            const float mxs = mx * sl2;
-            // pass 2: p = 2^(s*scale*log2e - max), row sum, P (bf16 pairs) written over the consumed S columns
-            float sum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < static_cast<int>(KV_ROWS) / 16; ++c) {
-                uint32_t r[16], pk[8];
-                tmem_ld16(trow + c * 16, r);
-                tmem_ld_wait();
+                for (int c = 0; c < 6; c += 2) {
+                    tmem_ld32(trow + (c + 1) * 32, rb);
+                    if ((c + 1) * 32 <= Lkp) softmax_max32(ra, mx);
+                    else {
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const float p0 = c * 16 + j < Lkp ? ex2f(fmaf(__uint_as_float(r[j]), sl2, -mxs)) : 0.f;
-                    const float p1 = c * 16 + j + 1 < Lkp ? ex2f(fmaf(__uint_as_float(r[j + 1]), sl2, -mxs)) : 0.f;
-                    sum += p0 + p1;
-                    pk[j >> 1] = pack_bf16x2(p0, p1);
+                        for (int j = 0; j < 32; ++j) if (c * 32 + j < Lkp) mx = fmaxf(mx, __uint_as_float(ra[j]));
+                    }
+                    tmem_ld_wait_dep(rb);
+                    if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
+                    if ((c + 2) * 32 <= Lkp) softmax_max32(rb, mx);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if ((c + 1) * 32 + j < Lkp) mx = fmaxf(mx, __uint_as_float(rb[j]));
+                    }
+                    tmem_ld_wait_dep(ra);
                 }
-                tmem_st8(trow + P_COL + c * 8, pk);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (192 + j < Lkp) mx = fmaxf(mx, __uint_as_float(ra[j]));
+                const float mxs = mx * sl2;
+                // ---- pass 2: p = 2^(s*scale*log2e - max), row sum, P (bf16 pairs) written over the already consumed S columns
+                float sum = 0.f;
+                uint32_t pk[16];
+                tmem_ld32(trow, ra);
+                tmem_ld_wait_dep(ra);
+#pragma unroll
+                for (int c = 0; c < 6; c += 2) {
+                    tmem_ld32(trow + (c + 1) * 32, rb);
+                    if ((c + 1) * 32 <= Lkp) softmax_exp32(ra, pk, sl2, mxs, sum);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float p0 = c * 32 + j < Lkp ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
+                            const float p1 = c * 32 + j + 1 < Lkp ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
+                            sum += p0 + p1;
+                            pk[j >> 1] = pack_bf16x2(p0, p1);
+                        }
+                    }
+                    tmem_ld_wait_dep(rb);
+                    tmem_st16(trow + P_COL + c * 16, pk);
+                    if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
+                    if ((c + 2) * 32 <= Lkp) softmax_exp32(rb, pk, sl2, mxs, sum);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float p0 = (c + 1) * 32 + j < Lkp ? ex2f(fmaf(__uint_as_float(rb[j]), sl2, -mxs)) : 0.f;
+                            const float p1 = (c + 1) * 32 + j + 1 < Lkp ? ex2f(fmaf(__uint_as_float(rb[j + 1]), sl2, -mxs)) : 0.f;
+                            sum += p0 + p1;
+                            pk[j >> 1] = pack_bf16x2(p0, p1);
+                        }
+                    }
+                    tmem_ld_wait_dep(ra);
+                    tmem_st16(trow + P_COL + (c + 1) * 16, pk);
+                }
+                {
+                    uint32_t pt[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        const float p0 = 192 + j < Lkp ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
+                        const float p1 = 192 + j + 1 < Lkp ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
+                        sum += p0 + p1;
+                        pt[j >> 1] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st8(trow + P_COL + 96, pt);
+                }
+                tmem_st_wait();
+                inv = 1.0f / sum;
             }
-            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_bar(t));
-            const float inv = 1.0f / sum;
-            // epilogue: O_t / sum -> bf16 -> one 128-byte row per thread
+            // ---- epilogue: O_t / sum -> bf16 -> one 128-byte row per thread
             mbar_wait(o_bar(t), it & 1);
             tc_fence_after();
             uint32_t o0[32], o1[32];
-            tmem_ld32(trow + O_COL, o0);
-            tmem_ld32(trow + O_COL + 32, o1);
-            tmem_ld_wait();
+            if (rows_live) {
+                tmem_ld32(trow + O_COL, o0);
+                tmem_ld32(trow + O_COL + 32, o1);
+                tmem_ld_wait();
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(free_bar(t));                // TMEM columns of tile t may be overwritten by the next problem
-            if (row < d.Lq) {
+            if (rows_live && row < d.Lq) {
                 const int h = prob % d.n_heads;
                 const int i = (prob / d.n_heads) % d.n_inner;
                 const int o = prob / (d.n_heads * d.n_inner);
@@ -248,8 +352,26 @@ int launch_tc(const Desc &d, cudaStream_t st) {
     }
     const int64_t n_prob = static_cast<int64_t>(d.n_outer) * d.n_inner * d.n_heads;
     SFB_CHECK_ARG(n_prob < (1ll << 31), "sfb_attention: too many problems");
+    // TMA staging needs every problem's rows on one regular 2D grid: outer / inner strides must be whole rows
+    const bool regular = d.q_row > 0 && d.kv_row > 0 && d.q_outer % d.q_row == 0 && d.q_inner % d.q_row == 0 && d.kv_outer % d.kv_row == 0 &&
+                         d.kv_inner % d.kv_row == 0 && d.q_row >= d.n_heads * HD && d.kv_row >= d.n_heads * HD;
+    static const bool tma_enabled = !(getenv("SFB_ATTN_TMA") && atoi(getenv("SFB_ATTN_TMA")) == 0);
+    CUtensorMap tq, tk, tv;
+    memset(&tq, 0, sizeof(tq)), memset(&tk, 0, sizeof(tk)), memset(&tv, 0, sizeof(tv));
+    int use_tma = 0, qo = 0, qi = 0, ko = 0, ki = 0;
+    if (regular && tma_enabled) {
+        qo = static_cast<int>(d.q_outer / d.q_row), qi = static_cast<int>(d.q_inner / d.q_row);
+        ko = static_cast<int>(d.kv_outer / d.kv_row), ki = static_cast<int>(d.kv_inner / d.kv_row);
+        const int64_t q_rows = static_cast<int64_t>(d.n_outer - 1) * qo + static_cast<int64_t>(d.n_inner - 1) * qi + d.Lq;
+        const int64_t kv_rows = static_cast<int64_t>(d.n_outer - 1) * ko + static_cast<int64_t>(d.n_inner - 1) * ki + d.Lk;
+        int rc = encode_tmap_bf16_2d(&tq, d.q, q_rows, d.n_heads * HD, d.q_row, d.Lq, HD);
+        if (rc == SFB_OK) rc = encode_tmap_bf16_2d(&tk, d.k, kv_rows, d.n_heads * HD, d.kv_row, d.Lk, HD);
+        if (rc == SFB_OK) rc = encode_tmap_bf16_2d(&tv, d.v, kv_rows, d.n_heads * HD, d.kv_row, d.Lk, HD);
+        if (rc != SFB_OK) return rc;
+        use_tma = 1;
+    }
     const unsigned grid = static_cast<unsigned>(n_prob < num_sms() ? n_prob : num_sms());
-    attn_space_tc_kernel<<<grid, kThreadsTc, SMEM_TC, st>>>(d, static_cast<int>(n_prob));
+    attn_space_tc_kernel<<<grid, kThreadsTc, SMEM_TC, st>>>(tq, tk, tv, d, static_cast<int>(n_prob), use_tma, qo, qi, ko, ki);
     SFB_CHECK_LAUNCH();
     return SFB_OK;
 }
