@@ -7,7 +7,7 @@
 //                          mma.sync.m16n8k16 (bf16 in, fp32 accumulate) for QK^T and PV and a register-resident online
 //                          softmax (quad shuffles only).  Space attention 196x197, AST 74x74, sync 198x198 (hd 96).
 //   attn_time_mma_kernel   Lq = Lk = 8 + CLS prefix, hd 64 (Motionformer time attention): two locations per block-diagonal
-//                          m16n8k16 problem, one warp per head, persistent double-buffered cp.async staging.
+//                          m16n8k16 problem, one warp per head, one CTA per location pair (two resident per SM).
 //   attn_time_kernel       the same on CUDA cores (one thread per (query frame, head)); kept for odd location counts.
 //   attn_row1_kernel       Lq = 1, hd 64 (Motionformer CLS query 1x1569, aggregator CLS rows 1x197 / 1x13): one CTA per problem,
 //                          8 lanes per key row, 32 private online-softmax states merged through shared memory.
@@ -456,57 +456,49 @@ __global__ void __launch_bounds__(HD == 64 ? 512 : 416) attn_mma_kernel(const De
 }
 
 // --------------------------------------------------------------- Motionformer time attention on tensor cores
-// Lq = Lk = 8 frames + CLS prefix key, hd 64.  A persistent CTA handles one PAIR of spatial locations for all heads per
-// iteration (one warp per head): the 16 x (3 * n_heads * 64) tile [2 locations x 8 frames] x [q | k | v] is staged with cp.async
-// (double-buffered, fully coalesced 1.5 KB row pieces), and the two 8 x 9 attentions of a pair are evaluated as ONE block-
+// Lq = Lk = 8 frames + CLS prefix key, hd 64.  One CTA handles one PAIR of spatial locations for all heads (one warp per head,
+// two CTAs per SM so one loads while the other computes): the 16 x (3 * n_heads * 64) tile [2 locations x 8 frames] x [q | k | v] is
+// staged with cp.async (fully coalesced 1.5 KB row pieces), and the two 8 x 9 attentions of a pair are evaluated as ONE block-
 // diagonal m16n8k16 problem: S = [Q_a; Q_b] [K_a | K_b | k_cls]^T keeps the two diagonal 8 x 8 blocks and the CLS column,
 // O = P V with P zero off the diagonal blocks.  28 mma.sync per (pair, head) instead of 2 x 9 x 64 x 2 x 8 CUDA-core FMAs.
-__global__ void __launch_bounds__(512) attn_time_mma_kernel(const Desc d, int n_pairs_total) {
+template <int H>   // heads == warps per CTA
+__global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) {
     constexpr int HD = 64;
     extern __shared__ __align__(16) uint8_t smem[];
-    const int H = d.n_heads;
-    const int seg_bytes = H * HD * 2;                 // one of q / k / v for one token, all heads
-    const int PITCH = 3 * seg_bytes + 16;             // +16: ldmatrix rows land on distinct bank groups
-    const int cls_off = 16 * PITCH;                   // [k_cls | v_cls] of the segment
-    const uint32_t buf_bytes = static_cast<uint32_t>(cls_off + 2 * seg_bytes + 16);
+    constexpr int seg_bytes = H * HD * 2;             // one of q / k / v for one token, all heads
+    constexpr int PITCH = 3 * seg_bytes + 16;         // +16: ldmatrix rows land on distinct bank groups
+    constexpr int cls_off = 16 * PITCH;               // [k_cls | v_cls] of the segment
+    constexpr int chunks_seg = seg_bytes / 16;
     const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;       // warp == head
     const int g = lane >> 2, t4 = lane & 3;
     const int pairs_per_outer = d.n_inner / 2;
-    const int chunks_seg = seg_bytes / 16;
-
-    auto issue_loads = [&](int pair, int bsel) {
-        const int o = pair / pairs_per_outer;
-        const int i0 = (pair % pairs_per_outer) * 2;
-        const uint32_t sb = s0 + bsel * buf_bytes;
-        for (int c = tid; c < 16 * 3 * chunks_seg; c += nthr) {
-            const int cc = c % chunks_seg;
-            const int part = (c / chunks_seg) % 3;    // 0 q, 1 k, 2 v
-            const int r = c / (3 * chunks_seg);       // 0..15 = location (r >> 3), frame (r & 7)
-            const int64_t tok = static_cast<int64_t>(i0 + (r >> 3));
-            const __nv_bfloat16 *src = part == 0 ? d.q + o * d.q_outer + tok * d.q_inner + static_cast<int64_t>(r & 7) * d.q_row
-                                                 : (part == 1 ? d.k : d.v) + o * d.kv_outer + tok * d.kv_inner + static_cast<int64_t>(r & 7) * d.kv_row;
-            cp_async16(sb + r * PITCH + part * seg_bytes + cc * 16, src + cc * 8);
+    const int pair = blockIdx.x;                      // one CTA per pair of locations; two CTAs per SM overlap load and math
+    const int o = pair / pairs_per_outer;
+    const int i0p = (pair % pairs_per_outer) * 2;
+    // 48 (row, part) segments of seg_bytes each + the CLS k / v segments: warp-uniform source pointers, lanes walk the 16-byte chunks
+    for (int sgm = warp; sgm < 50; sgm += H) {
+        const __nv_bfloat16 *src;
+        uint32_t dst;
+        if (sgm < 48) {
+            const int r = sgm / 3, part = sgm % 3;    // r = location (r >> 3), frame (r & 7); part 0 q, 1 k, 2 v
+            const int64_t tok = static_cast<int64_t>(i0p + (r >> 3));
+            src = part == 0 ? d.q + o * d.q_outer + tok * d.q_inner + static_cast<int64_t>(r & 7) * d.q_row
+                            : (part == 1 ? d.k : d.v) + o * d.kv_outer + tok * d.kv_inner + static_cast<int64_t>(r & 7) * d.kv_row;
+            dst = s0 + r * PITCH + part * seg_bytes;
+        } else {
+            src = (sgm == 48 ? d.kp : d.vp) + o * d.prefix_outer;
+            dst = s0 + cls_off + (sgm - 48) * seg_bytes;
         }
-        for (int c = tid; c < 2 * chunks_seg; c += nthr) {
-            const int cc = c % chunks_seg, part = c / chunks_seg;
-            cp_async16(sb + cls_off + part * seg_bytes + cc * 16, (part == 0 ? d.kp : d.vp) + o * d.prefix_outer + cc * 8);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
+        for (int cc = lane; cc < chunks_seg; cc += 32) cp_async16(dst + cc * 16, src + cc * 8);
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     const float sl2 = d.scale * 1.4426950408889634f;
-    int bsel = 0;
-    if (static_cast<int>(blockIdx.x) < n_pairs_total) issue_loads(blockIdx.x, 0);
-    for (int pair = blockIdx.x; pair < n_pairs_total; pair += gridDim.x) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        const int next = pair + gridDim.x;
-        if (next < n_pairs_total) issue_loads(next, bsel ^ 1);
-
-        if (warp < H) {
-            const uint32_t sb = s0 + bsel * buf_bytes;
+    {
+        {
+            const uint32_t sb = s0;
             const uint32_t hq = sb + warp * (HD * 2), hk = hq + seg_bytes, hv = hk + seg_bytes;
             const uint32_t ck = sb + cls_off + warp * (HD * 2), cv = ck + seg_bytes;
             float s[3][4];
@@ -559,15 +551,13 @@ __global__ void __launch_bounds__(512) attn_time_mma_kernel(const Desc d, int n_
             }
             // stage the 16 x 64 output in this head's (dead) Q columns, then 16-byte coalesced stores
             __syncwarp();
-            uint8_t *so = smem + bsel * buf_bytes + warp * (HD * 2);
+            uint8_t *so = smem + warp * (HD * 2);
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 *reinterpret_cast<uint32_t *>(so + g * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][0], oacc[n][1]);
                 *reinterpret_cast<uint32_t *>(so + (g + 8) * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][2], oacc[n][3]);
             }
             __syncwarp();
-            const int o = pair / pairs_per_outer;
-            const int i0p = (pair % pairs_per_outer) * 2;
             __nv_bfloat16 *og = d.out + o * d.o_outer + warp * HD;
 #pragma unroll
             for (int c = lane; c < 16 * 8; c += 32) {
@@ -576,9 +566,7 @@ __global__ void __launch_bounds__(512) attn_time_mma_kernel(const Desc d, int n_
                     *reinterpret_cast<const uint4 *>(so + r * PITCH + cc * 16);
             }
         }
-        bsel ^= 1;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace attn
@@ -658,22 +646,20 @@ extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
         SFB_CHECK_LAUNCH();
         return SFB_OK;
     }
-    if (desc->impl == 0 && aligned16 && HD == 64 && d.Lq == 8 && d.Lk == 8 && d.has_prefix && d.n_inner % 2 == 0 && d.n_heads <= 16) {
-        const int seg_bytes = d.n_heads * 64 * 2;
-        const int smem_bytes = 2 * (16 * (3 * seg_bytes + 16) + 2 * seg_bytes + 16);
-        if (smem_bytes <= 220 * 1024) {
-            static int cur = 0;
-            if (smem_bytes > cur) {
-                SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_time_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-                cur = smem_bytes;
-            }
-            const int64_t n_pairs = static_cast<int64_t>(d.n_outer) * (d.n_inner / 2);
-            SFB_CHECK_ARG(n_pairs < (1ll << 31), "sfb_attention: too many problems");
-            const unsigned grid = static_cast<unsigned>(n_pairs < num_sms() ? n_pairs : num_sms());
-            attn_time_mma_kernel<<<grid, 32 * d.n_heads, smem_bytes, st>>>(d, static_cast<int>(n_pairs));
-            SFB_CHECK_LAUNCH();
-            return SFB_OK;
+    if (desc->impl == 0 && aligned16 && HD == 64 && d.Lq == 8 && d.Lk == 8 && d.has_prefix && d.n_inner % 2 == 0 && d.n_heads == 12) {
+        constexpr int H = 12;
+        constexpr int seg_bytes = H * 64 * 2;
+        constexpr int smem_bytes = 16 * (3 * seg_bytes + 16) + 2 * seg_bytes + 16;       // 77 KB: two CTAs per SM
+        static bool attr_set = false;
+        if (!attr_set) {
+            SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_time_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            attr_set = true;
         }
+        const int64_t n_pairs = static_cast<int64_t>(d.n_outer) * (d.n_inner / 2);
+        SFB_CHECK_ARG(n_pairs < (1ll << 31), "sfb_attention: too many problems");
+        attn_time_mma_kernel<H><<<static_cast<unsigned>(n_pairs), 32 * H, smem_bytes, st>>>(d);
+        SFB_CHECK_LAUNCH();
+        return SFB_OK;
     }
     if (desc->impl == 0 && aligned16 && HD == 64 && d.Lq == 8 && d.Lk == 8 && d.has_prefix && d.n_heads % 4 == 0) {
         const int64_t warps = static_cast<int64_t>(d.n_outer) * d.n_inner * (d.n_heads / 4);

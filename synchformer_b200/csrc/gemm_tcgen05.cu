@@ -166,12 +166,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-                int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CG) + rank * BLOCK_M;
-                int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + rank * C::B_ROWS * (CG - 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CG) + rank * BLOCK_M;
+            int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + rank * C::B_ROWS * (CG - 1);
+            if (lane == 0) {
                 // a box that lies completely outside the matrix (second CTA of a pair on a ragged edge) loads rows 0.. instead:
                 // its products only reach accumulator rows / columns that the epilogue masks
                 if (m0 >= p.M) m0 = 0;
@@ -195,6 +195,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (pair leader only) ================

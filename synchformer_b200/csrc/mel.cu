@@ -5,7 +5,7 @@
 //   dataset/transforms.py:861-871  (x - (-4.2677393)) / (2 * 4.5689974)
 // One CTA per (segment, STFT frame).  The periodic Hann(400) window sits at samples [312, 712) of the 1024-sample
 // frame, so only 400 products per bin are non-zero: a direct 400-term DFT for bins 0..512 with a 1024-entry
-// twiddle table in shared memory, accumulated in fp64 (a pure tone leaves most bins ~1e-8 of the peak, and
+// twiddle table in shared memory (bins k and 512-k computed together), accumulated in fp64 (a pure tone leaves most bins ~1e-8 of the peak, and
 // log(x + 1e-6) exposes fp32 summation error there).  |X|^2 is invariant to the 312-sample phase offset.
 // The 513 x 128 HTK triangle filterbank (L2-resident, 262 KB) is applied from shared-memory power values.
 #include <math.h>
@@ -23,31 +23,39 @@ __device__ double2 g_twiddle[N_FFT];       // (cos, sin)(2 pi j / 1024)
 __device__ float g_window[WIN];
 __device__ float g_fb[N_FREQ * N_MEL];     // [freq][mel]
 
-__global__ void __launch_bounds__(256) mel_kernel(const float *__restrict__ wave, float *__restrict__ out) {
+// X[k] and X[512 - k] share their twiddles: e^{-2 pi i (512-k) n / 1024} = (-1)^n e^{+2 pi i k n / 1024}.  With the sums over even
+// and odd n kept apart, one walk over the 400 windowed samples yields both bins: X[k] = (Ae + Ao) - i (Be + Bo),
+// X[512-k] = (Ae - Ao) + i (Be - Bo).  Threads 0..256 own the pairs (k, 512 - k).
+constexpr int MEL_THREADS = 288;
+
+__global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float *__restrict__ wave, float *__restrict__ out) {
     __shared__ double2 tw[N_FFT];
     __shared__ float xs[WIN];
     __shared__ float pw[N_FREQ + 3];
     const int frame = blockIdx.x % N_FRAMES;
     const int64_t seg = blockIdx.x / N_FRAMES;
     const int tid = threadIdx.x;
-    for (int j = tid; j < N_FFT; j += 256) tw[j] = g_twiddle[j];
+    for (int j = tid; j < N_FFT; j += MEL_THREADS) tw[j] = g_twiddle[j];
     const float *w = wave + seg * SEG;
-    for (int n = tid; n < WIN; n += 256) {
+    for (int n = tid; n < WIN; n += MEL_THREADS) {
         int idx = frame * HOP + WIN_OFF + n - N_FFT / 2;          // index into the un-padded segment
         idx = idx < 0 ? -idx : (idx >= SEG ? 2 * (SEG - 1) - idx : idx);   // reflect padding (torch.stft center=True)
         xs[n] = __ldg(w + idx) * g_window[n];
     }
     __syncthreads();
-    for (int k = tid; k < N_FREQ; k += 256) {
-        double re = 0.0, im = 0.0;
+    if (tid <= N_FFT / 4) {
+        const int k = tid;
+        double ae = 0.0, be = 0.0, ao = 0.0, bo = 0.0;
 #pragma unroll 4
-        for (int n = 0; n < WIN; ++n) {
-            const double2 c = tw[(k * n) & (N_FFT - 1)];
-            const double x = static_cast<double>(xs[n]);
-            re = fma(x, c.x, re);
-            im = fma(x, c.y, im);
+        for (int n = 0; n < WIN; n += 2) {
+            const double2 c0 = tw[(k * n) & (N_FFT - 1)], c1 = tw[(k * (n + 1)) & (N_FFT - 1)];
+            const double x0 = static_cast<double>(xs[n]), x1 = static_cast<double>(xs[n + 1]);
+            ae = fma(x0, c0.x, ae), be = fma(x0, c0.y, be);
+            ao = fma(x1, c1.x, ao), bo = fma(x1, c1.y, bo);
         }
-        pw[k] = static_cast<float>(re * re + im * im);
+        const double r0 = ae + ao, i0 = be + bo, r1 = ae - ao, i1 = be - bo;
+        pw[k] = static_cast<float>(r0 * r0 + i0 * i0);
+        pw[N_FFT / 2 - k] = static_cast<float>(r1 * r1 + i1 * i1);   // k = 256 writes the same bin twice with the same value
     }
     __syncthreads();
     if (tid < N_MEL) {
@@ -101,7 +109,7 @@ extern "C" int sfb_mel_frontend(const float *wave, float *out, int n_seg, void *
     SFB_CHECK_ARG(wave && out && n_seg > 0, "sfb_mel_frontend: bad arguments");
     int rc = init_tables();   // first call only: three small host->device table uploads
     if (rc != SFB_OK) return rc;
-    mel_kernel<<<static_cast<unsigned>(static_cast<int64_t>(n_seg) * N_FRAMES), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wave, out);
+    mel_kernel<<<static_cast<unsigned>(static_cast<int64_t>(n_seg) * N_FRAMES), MEL_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wave, out);
     SFB_CHECK_LAUNCH();
     return SFB_OK;
 }
