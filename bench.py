@@ -261,6 +261,11 @@ def main():
         value = B * world * args.steps / (ms / 1e3)
         e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        traffic, traffic_note = None, None
+        tp = os.path.join(REPO, 'profiles', 'r1_gemm_traffic.json')
+        if os.path.exists(tp):                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu capture
+            tj = json.load(open(tp))
+            traffic, traffic_note = tj['dram_bytes'], f"{tj['launch']}; algorithmic bytes {tj['algorithmic_bytes']}; {tj['source']}"
         result = {
             'metric': 'clips/sec offset inference (5s-style clip: S x 0.64 s segments, 224p RGB + 16 kHz)', 'value': value, 'unit': 'clips/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -270,7 +275,8 @@ def main():
                        'l2_policy': 'inputs larger than L2 (2.47 GB fp16 video per rank); activations stream through HBM',
                        'weights': 'synthetic_state_dict(seed 1337), random-init-like, non-zero patch embedding'},
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
-                         'frac': (achieved / peaks['sustained']) if achieved else None, 'traffic': None,
+                         'frac': (achieved / peaks['sustained']) if achieved else None, 'traffic': traffic, 'traffic_launch': traffic_note,
+                         'achieved_def': 'sum over the GEMM launches of the timed steps of 2*M*N*K / sum of their CUDA-event durations',
                          'kernel': 'gemm_bf16_tcgen05_kernel', 'launches_timed': gemm_n, 'gemm_ms_per_step': gemm_ms / args.steps,
                          'peak_source': peaks['source'] + ', sustained bf16 (kernel timed inside a long step)',
                          'step_frac_canonical': value * flops_per_clip(S) / world / (peaks['sustained'] * 1e12),
