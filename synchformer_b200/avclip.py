@@ -1,0 +1,49 @@
+"""Stage-I contrastive forward around the same two encoders (BASELINE.json config 3).
+
+Mirrors `AVCLIP.forward` of the reference (model/modules/feat_extractors/train_clip_src/open_clip/model.py:449-545) for the
+forward pass in eval / no_grad: encoders with `agg_time_module='AveragePooling'` -> (B*S, 768) -> identity bridges
+(`DoNothingBridge`, configs/segment_avclip.yaml:45-54) -> L2 normalise -> similarities / logit_scale -> symmetric cross-entropy with
+identity targets.  Inputs come in the STAGE-I layouts: rgb (B, S, C=3, T=16, H, W), audio (B, S, T=66, F=128)
+(segment_avclip.yaml:208-211).  The encoders are the kernel-backed `MotionFormer` / `AST` of model.py; the 128 x 128 similarity tail is
+three tiny torch ops (normalise, matmul, cross_entropy) - plumbing next to 52 TFLOP of encoder work.
+The backward of the encoders (the actual stage-I training step) is out of scope for this round.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .model import AST, MotionFormer
+
+
+class AVCLIP(nn.Module):
+    def __init__(self, n_embd: int = 768, init_scale: float = 0.07, clamp_scale_min: float = 0.001, clamp_scale_max: float = 0.5):
+        super().__init__()
+        self.n_embd = n_embd
+        self.v_encoder = MotionFormer(extract_features=True, factorize_space_time=True, agg_space_module='TransformerEncoderLayer',
+                                      agg_time_module='AveragePooling', add_global_repr=False)
+        self.a_encoder = AST(extract_features=True, max_spec_t=66, factorize_freq_time=True, agg_freq_module='TransformerEncoderLayer',
+                             agg_time_module='AveragePooling', add_global_repr=False)
+        self.vproj, self.aproj = nn.Identity(), nn.Identity()            # model.modules.bridges.DoNothingBridge
+        self.clamp_scale_min, self.clamp_scale_max = clamp_scale_min, clamp_scale_max
+        self.logit_scale = nn.Parameter(torch.ones([]) * init_scale)
+
+    def encode_streams(self, vis: torch.Tensor, aud: torch.Tensor, do_norm: bool = True):
+        """open_clip/model.py:529-545: (B*S, 768) visual and audio segment features."""
+        v, _ = self.v_encoder(vis)                 # (B, S, 768)
+        a, _ = self.a_encoder(aud)
+        v, a = v.reshape(-1, self.n_embd), a.reshape(-1, self.n_embd)
+        if do_norm:
+            v, a = F.normalize(v, dim=-1), F.normalize(a, dim=-1)
+        return v, a
+
+    @torch.no_grad()
+    def forward(self, vis: torch.Tensor, aud: torch.Tensor, alpha: float = 0.0, for_loop: bool = False, world_size: int = 1):
+        assert alpha == 0.0, f'alpha={alpha} not supported yet'          # same assertion as the reference (:489)
+        scale = self.logit_scale.clamp(self.clamp_scale_min, self.clamp_scale_max)
+        vfeat, afeat = self.encode_streams(vis, aud)
+        sim_v2a = vfeat @ afeat.mT / self.logit_scale                     # compute_loss :507-513
+        sim_a2v = afeat @ vfeat.mT / self.logit_scale
+        tgt = torch.eye(*sim_v2a.shape, device=sim_v2a.device, dtype=sim_v2a.dtype)
+        loss = (F.cross_entropy(sim_v2a, tgt) + F.cross_entropy(sim_a2v, tgt)) / 2
+        return {'rgb_features': (vfeat, None), 'audio_features': (afeat, None), 'logit_scales': scale,
+                'losses': {'segment_contrastive_loss': loss}}

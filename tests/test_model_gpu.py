@@ -151,3 +151,67 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libsynchformer_b200.so')
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         _lib.load()
+
+
+def test_config1_single_clip_14_segments(cuda_device):
+    """BASELINE.json config 1: one synthetic 5 s clip = 14 overlapping segments (block_shape [198]), example.py-style call
+    `model(vid, aud)` with fp16 video, against the CPU oracle."""
+    from oracle import synchformer_oracle as O
+    from synchformer_b200 import model as M, ops, synth
+    B, S = 1, 14
+    sd = synth.synthetic_state_dict(1337, n_segments=S)
+    model = M.build_synchformer(n_segments=S, state_dict=sd, device=cuda_device)
+    vis = synth.synthetic_video(B, S, seed=2).half()
+    wave = synth.synthetic_waveform(B, S, seed=2)
+    with torch.no_grad():
+        mel = ops.mel_frontend(wave.cuda())
+        loss, logits = model(vis.cuda(), mel.unsqueeze(2))
+    assert loss is None and logits.shape == (1, 21) and logits.dtype == torch.float32
+    _, ref = O.forward(sd, vis.float(), O.mel_frontend(wave).float().unsqueeze(2))
+    assert (logits.cpu() - ref).abs().max() <= LOGIT_ABS
+    assert rel_l2(logits, ref) <= LOGIT_REL
+    assert torch.equal(logits.argmax(-1).cpu(), ref.argmax(-1))
+
+
+def test_syncability_head_variant_matches_oracle(cuda_device):
+    """GlobalTransformerWithSyncabilityHead (sync_model.py:176-190, configs/ft_synchability.yaml): 2-class head on the same stem."""
+    from oracle import synchformer_oracle as O
+    from synchformer_b200 import model as M, synth
+    B, S = 2, 2
+    cfg = M.sync_yaml_model_config(n_segments=S, transformer_target='model.sync_model.GlobalTransformerWithSyncabilityHead')
+    cfg = {k: {kk: vv for kk, vv in v.items() if kk != 'is_trainable'} for k, v in cfg.items()}
+    model = M.Synchformer(**cfg)
+    sd = synth.synthetic_state_dict(21, n_segments=S, n_classes=2, head='sync_head')
+    model.load_state_dict(sd, strict=True)
+    model.eval().to(cuda_device)
+    g = torch.Generator().manual_seed(4)
+    vf, af = torch.randn(B, S, 8, 768, generator=g), torch.randn(B, S, 6, 768, generator=g)
+    with torch.no_grad():
+        v, a = model.project(vf.cuda(), af.cuda())
+        logits = model.transformer(v, a)
+    ref = O.sync_head(sd, vf, af, head='sync_head')
+    assert logits.shape == (B, 2)
+    assert (logits.cpu() - ref).abs().max() <= LOGIT_ABS
+
+
+def test_avclip_contrastive_forward_matches_oracle(cuda_device):
+    """BASELINE.json config 3 in miniature: segment_avclip.yaml encoders (time-average pooled), stage-I input layouts,
+    normalised features + symmetric contrastive loss (open_clip/model.py:474-527) against the CPU oracle."""
+    from oracle import synchformer_oracle as O
+    from synchformer_b200 import avclip, synth
+    B, S = 2, 2
+    sd = synth.synthetic_state_dict(8, n_segments=S)
+    model = avclip.AVCLIP().to(cuda_device).eval()
+    model.v_encoder.load_state_dict({k[len('vfeat_extractor.'):]: v for k, v in sd.items() if k.startswith('vfeat_extractor.')})
+    model.a_encoder.load_state_dict({k[len('afeat_extractor.'):]: v for k, v in sd.items() if k.startswith('afeat_extractor.')})
+    vis = synth.synthetic_video(B, S, seed=6)                                   # (B, S, T, C, H, W)
+    mel = O.mel_frontend(synth.synthetic_waveform(B, S, seed=6)).float()        # (B, S, F, T)
+    out = model(vis.permute(0, 1, 3, 2, 4, 5).cuda(), mel.permute(0, 1, 3, 2).cuda())      # stage-I layouts
+    v_ref, a_ref = O.avclip_features(sd, vis, mel.unsqueeze(2))
+    v, a = out['rgb_features'][0].cpu(), out['audio_features'][0].cpu()
+    assert v.shape == (B * S, 768) and a.shape == (B * S, 768)
+    assert rel_l2(v, v_ref) <= FEAT_TOL and rel_l2(a, a_ref) <= FEAT_TOL
+    sim = v_ref @ a_ref.T / 0.07
+    tgt = torch.eye(B * S)
+    loss_ref = (torch.nn.functional.cross_entropy(sim, tgt) + torch.nn.functional.cross_entropy(sim.T, tgt)) / 2
+    assert abs(float(out['losses']['segment_contrastive_loss']) - float(loss_ref)) < 5e-2 * max(1.0, abs(float(loss_ref)))
