@@ -103,18 +103,30 @@ __device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, u
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// commit of all prior MMAs of the pair, arriving on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(static_cast<uint16_t>(3))
+// commit of all prior MMAs of the pair, arriving on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
                  : "memory");
 }
+// TMA load multicast to the CTAs of `cta_mask` (same CTA-relative smem offset in each); with cta_group::2 the completion is
+// signalled on the barrier at `bar`'s offset in the LEADER of each destination CTA's pair (bar = local address with the peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_cg2_mc(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the bit that distinguishes the two CTAs of a pair in a shared-window address
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int CG>
+// CL = CTAs per cluster.  CL == 4 (with CG == 2): two CTA pairs stacked along M share every W tile - each CTA fetches a quarter of it
+// and multicasts it to the CTA of the same parity in the other pair, cutting L2->SM operand traffic from 64 to 48 bytes per MMA clock.
+template <int CG, int CL>
 __global__ void __launch_bounds__(kThreads, 1)   // 18 warps are allocated as 20 (granularity 4): 96 registers per thread
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const EpiParams p) {
+    static_assert(CL == CG || (CG == 2 && CL == 4), "cluster = one CTA, one pair, or two pairs");
     using C = Cfg<CG>;
+    constexpr int PAIRS = CL / CG;                    // CTA groups per cluster, stacked along M
     constexpr int kStages = C::kStages;
     constexpr uint32_t STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -123,7 +135,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;      // rank 0 of a pair is the MMA leader
+    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;     // rank in the cluster
+    const uint32_t rank = crank & 1u;                            // rank in the pair; 0 is the MMA leader
+    const uint32_t pair = crank >> 1;                            // which pair of the cluster
     const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -138,7 +152,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar(s), 1);     // the (leader's) producer arrive.expect_tx; TMA of both CTAs completes the bytes
-            mbar_init(empty_bar(s), 1);    // one tcgen05.commit (multicast to both CTAs when CG == 2)
+            mbar_init(empty_bar(s), PAIRS); // one tcgen05.commit per pair of the cluster (each pair also reads what the others multicast)
         }
         for (int a = 0; a < kAccStages; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -156,21 +170,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     }
     tc_fence_before();
-    if (CG == 2) cluster_sync_all(); else __syncthreads();       // barriers initialised + TMEM allocated in both CTAs
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // barriers initialised + TMEM allocated in every CTA of the cluster
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;       // tiles of (128 * CG) x 256
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
+    const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;     // a tile is (128 * CG * PAIRS) rows x 256 columns
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-            int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CG) + rank * BLOCK_M;
-            int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + rank * C::B_ROWS * (CG - 1);
+            int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CL) + crank * BLOCK_M;
+            int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + rank * C::B_ROWS * (CG - 1) +
+                     (PAIRS == 2 ? pair * (C::B_ROWS / 2) : 0);          // CL == 4: this CTA fetches one 64-row quarter of the W tile
             if (lane == 0) {
                 // a box that lies completely outside the matrix (second CTA of a pair on a ragged edge) loads rows 0.. instead:
                 // its products only reach accumulator rows / columns that the epilogue masks
@@ -180,10 +195,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = tiles_base + stage * STAGE_BYTES;
                     if (CG == 2) {
-                        const uint32_t fb = mapa_u32(full_bar(stage), 0);                     // the leader's barrier
-                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);   // bytes of both CTAs
+                        const uint32_t fb = full_bar(stage) & kPeerBitMask;                   // the pair leader's barrier
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);   // bytes landing in both CTAs of the pair
                         tma_load_2d_cg2(sa, &tmap_a, fb, kb * BLOCK_K, m0);
-                        tma_load_2d_cg2(sa + A_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+                        if (PAIRS == 2)     // quarter of the W tile -> same-parity CTA of both pairs
+                            tma_load_2d_cg2_mc(sa + A_BYTES + pair * (C::B_BYTES / 2), &tmap_w, fb, kb * BLOCK_K, n0,
+                                               static_cast<uint16_t>((1u << rank) | (1u << (rank + 2))));
+                        else
+                            tma_load_2d_cg2(sa + A_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
                     } else {
                         mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
                         tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m0);
@@ -218,13 +237,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, static_cast<uint32_t>((kb | k) != 0));
                         else umma_bf16(tmem_d, da, db, idesc, static_cast<uint32_t>((kb | k) != 0));
                     }
-                    if (CG == 2) umma_commit_cg2(empty_bar(stage)); else umma_commit(empty_bar(stage));   // smem stage reusable
+                    if (CG == 2) umma_commit_cg2(empty_bar(stage), static_cast<uint16_t>((1u << CL) - 1)); else umma_commit(empty_bar(stage));   // smem stage reusable
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                if (CG == 2) umma_commit_cg2(tfull_bar(acc)); else umma_commit(tfull_bar(acc));           // accumulator complete
+                if (CG == 2) umma_commit_cg2(tfull_bar(acc), static_cast<uint16_t>(3u << (2 * pair))); else umma_commit(tfull_bar(acc));   // accumulator complete (own pair)
                 if (++acc == kAccStages) {
                     acc = 0;
                     acc_phase ^= 1u;
@@ -246,11 +265,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int rr = lane >> 3, cc = lane & 7;              // read-back mapping: rows 4i + rr, 16-byte chunk cc
         int acc = 0;
         uint32_t acc_phase = 0;
-        const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(tempty_bar(0), 0) : tempty_bar(0);
+        const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(tempty_bar(0), crank & ~1u) : tempty_bar(0);
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-            const int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CG) + rank * BLOCK_M + q * 32;
+            const int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CL) + crank * BLOCK_M + q * 32;
             const int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + quarter * 64;
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + quarter * 64);
+            // The fp32 residual rows of this thread's read-back mapping do not depend on the accumulator: the first chunk's
+            // are requested BEFORE waiting for the MMAs of this tile, so their HBM latency hides behind the main loop; the
+            // second chunk's are requested as soon as the first chunk's registers are free (explicit registers: `out` may alias
+            // `residual`, so the compiler will not hoist these loads above earlier stores by itself).
+            float4 res[8];
+            auto load_res = [&](int c) {
+                const int gcol = n0 + c * 32 + cc * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t grow = m0 + 4 * i + rr;
+                    res[i] = (grow < p.M && gcol < p.N) ? *reinterpret_cast<const float4 *>(p.residual + grow * p.ldr + gcol)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            if (out_f32 && has_res) load_res(0);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             if (out_f32) {
@@ -258,18 +292,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int c = 0; c < 2; ++c) {
                     const int col0 = n0 + c * 32;
                     const int gcol = col0 + cc * 4;
-                    // residual rows for the read-back mapping, requested before the accumulator is even read so that the
-                    // HBM latency overlaps the TMEM load, bias and GELU (explicit registers: `out` may alias `residual`,
-                    // so the compiler will not move these loads above the stores of the previous chunk by itself)
-                    float4 res[8];
-                    if (has_res && col0 < p.N) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int64_t grow = m0 + 4 * i + rr;
-                            res[i] = (grow < p.M && gcol < p.N) ? *reinterpret_cast<const float4 *>(p.residual + grow * p.ldr + gcol)
-                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
                     uint32_t r[32];
                     tmem_ld32(tbase + c * 32, r);
                     tmem_ld_wait();
@@ -306,6 +328,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         }
                         __syncwarp();
                     }
+                    if (has_res && c == 0) load_res(1);
                 }
             } else {
                 const int col0 = n0;
@@ -462,46 +485,63 @@ extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const fl
         SFB_CHECK_LAUNCH();
         return SFB_OK;
     }
-    SFB_CHECK_ARG(impl == 0 || impl == 2 || impl == 3, "sfb_gemm_bf16: unknown impl %d (0 auto, 1 CUDA-core check, 2 single-CTA, 3 CTA-pair)", impl);
-    // CTA pairs (256-row tiles) unless the problem has at most one 128-row block
-    const int cg = impl == 2 ? 1 : impl == 3 ? 2 : (M > BLOCK_M ? 2 : 1);
+    SFB_CHECK_ARG(impl == 0 || impl == 2 || impl == 3 || impl == 4,
+                  "sfb_gemm_bf16: unknown impl %d (0 auto, 1 CUDA-core check, 2 single-CTA, 3 CTA-pair, 4 two pairs + W multicast)", impl);
+    // CTA pairs (256-row tiles) unless the problem has at most one 128-row block; clusters of two pairs when asked for
+    static const int cl_env = getenv("SFB_GEMM_CL") ? atoi(getenv("SFB_GEMM_CL")) : 2;
+    const int cg = impl == 2 ? 1 : (impl == 3 || impl == 4) ? 2 : (M > BLOCK_M ? 2 : 1);
+    const int cl = cg == 1 ? 1 : impl == 4 ? 4 : impl == 3 ? 2 : (cl_env == 4 && M > 2 * BLOCK_M ? 4 : 2);
 
     CUtensorMap tmap_a, tmap_w;
     int rc = make_tmap(&tmap_a, A, M, K, lda, BLOCK_M);
     if (rc != SFB_OK) return rc;
-    rc = make_tmap(&tmap_w, W, N, K, K, BLOCK_N / cg);
+    rc = make_tmap(&tmap_w, W, N, K, K, BLOCK_N / cl);           // rows of W fetched by one CTA per k-block
     if (rc != SFB_OK) return rc;
 
     if (cg == 1) {
         static bool attr_set = false;
         if (!attr_set) {
-            SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+            SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
             attr_set = true;
         }
         const int num_tiles = p.num_m_blocks * p.num_n_blocks;
         const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-        gemm_bf16_tcgen05_kernel<1><<<grid, kThreads, Cfg<1>::SMEM_BYTES, st>>>(tmap_a, tmap_w, p);
+        gemm_bf16_tcgen05_kernel<1, 1><<<grid, kThreads, Cfg<1>::SMEM_BYTES, st>>>(tmap_a, tmap_w, p);
         SFB_CHECK_LAUNCH();
         return SFB_OK;
     }
     static bool attr_set2 = false;
     if (!attr_set2) {
-        SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+        SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+        SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
         attr_set2 = true;
     }
-    p.num_m_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);             // 256-row pair tiles
+    p.num_m_blocks = (M + cl * BLOCK_M - 1) / (cl * BLOCK_M);           // 256-row (pair) or 512-row (two pairs) tiles
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-    const int max_pairs = num_sms() / 2;
-    const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = cl, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2>, tmap_a, tmap_w, p));
+    int max_clusters = num_sms() / cl;
+    if (cl == 4) {      // 4-CTA clusters do not tile every GPC: ask how many can be co-resident
+        static int cached = 0;
+        if (cached == 0) {
+            cfg.gridDim = dim3(cl * (num_sms() / cl));
+            int n = 0;
+            SFB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_bf16_tcgen05_kernel<2, 4>, &cfg));
+            cached = n > 0 ? n : 1;
+        }
+        max_clusters = cached < max_clusters ? cached : max_clusters;
+    }
+    const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+    cfg.gridDim = dim3(cl * clusters);
+    if (cl == 4)
+        SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2, 4>, tmap_a, tmap_w, p));
+    else
+        SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2, 2>, tmap_a, tmap_w, p));
     return SFB_OK;
 }

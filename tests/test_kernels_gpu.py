@@ -25,7 +25,7 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(2, id='tc1cta'), pytest.param(3, id='tcpair'), pytest.param(1, id='simple')])
+@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(2, id='tc1cta'), pytest.param(3, id='tcpair'), pytest.param(4, id='tcquad'), pytest.param(1, id='simple')])
 @pytest.mark.parametrize('M,N,K', GEMM_SHAPES)
 def test_gemm_bias(cuda_device, impl, M, N, K):
     from synchformer_b200 import ops
