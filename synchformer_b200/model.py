@@ -502,6 +502,42 @@ class Synchformer(nn.Module):
         return super().load_state_dict(sd, strict)
 
 
+class GraphedForward:
+    """CUDA-graph replay of `Synchformer.forward` for one fixed input shape (small-batch latency: the forward is ~290 kernel launches,
+    which at B = 1 are launch-bound when issued one by one from Python).  Inputs are copied into static device buffers, the captured
+    graph is replayed on the current stream, and the static logits tensor is returned (valid until the next call).
+
+        fwd = GraphedForward(model, vis_example, aud_example)
+        logits = fwd(vis, aud)          # same shapes / dtypes as the examples
+    """
+
+    def __init__(self, model: 'Synchformer', vis: torch.Tensor, aud: torch.Tensor, warmup: int = 2):
+        ops.require_cuda(vis, 'vis')
+        self.model = model
+        self.vis = torch.empty_like(vis)
+        self.aud = torch.empty_like(aud)
+        self.vis.copy_(vis)
+        self.aud.copy_(aud)
+        stream = torch.cuda.Stream(device=vis.device)
+        stream.wait_stream(torch.cuda.current_stream(vis.device))
+        with torch.cuda.stream(stream), torch.no_grad():
+            for _ in range(max(1, warmup)):                     # weight caches, function attributes, constant tables: all set up before capture
+                model(self.vis, self.aud)
+        torch.cuda.current_stream(vis.device).wait_stream(stream)
+        torch.cuda.synchronize(vis.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            _, self.logits = model(self.vis, self.aud)
+
+    def __call__(self, vis: torch.Tensor, aud: torch.Tensor) -> torch.Tensor:
+        if vis.shape != self.vis.shape or aud.shape != self.aud.shape or vis.dtype != self.vis.dtype or aud.dtype != self.aud.dtype:
+            raise ValueError(f'graph was captured for {tuple(self.vis.shape)} {self.vis.dtype} / {tuple(self.aud.shape)} {self.aud.dtype}')
+        self.vis.copy_(vis, non_blocking=True)
+        self.aud.copy_(aud, non_blocking=True)
+        self.graph.replay()
+        return self.logits
+
+
 def sync_yaml_model_config(n_segments: int = 14, n_classes: int = 21, transformer_target: str = 'model.sync_model.GlobalTransformer') -> dict:
     """The `model.params` tree of configs/sync.yaml:6-59 with interpolations resolved, as plain dicts."""
     return dict(

@@ -215,3 +215,38 @@ def test_avclip_contrastive_forward_matches_oracle(cuda_device):
     tgt = torch.eye(B * S)
     loss_ref = (torch.nn.functional.cross_entropy(sim, tgt) + torch.nn.functional.cross_entropy(sim.T, tgt)) / 2
     assert abs(float(out['losses']['segment_contrastive_loss']) - float(loss_ref)) < 5e-2 * max(1.0, abs(float(loss_ref)))
+
+
+def test_cuda_graph_replay_matches_eager_launches(cuda_device):
+    """The whole forward captured into one CUDA graph (small-batch latency path) returns bit-identical logits, also on new inputs."""
+    import time
+    from synchformer_b200 import model as M, synth
+    B, S = 1, 14
+    model = M.build_synchformer(n_segments=S, state_dict=synth.synthetic_state_dict(1337, n_segments=S), device=cuda_device)
+    g = torch.Generator(device='cuda').manual_seed(1)
+    vis = (torch.rand(B, S, 16, 3, 224, 224, device='cuda', generator=g) * 2 - 1).half()
+    aud = torch.randn(B, S, 1, 128, 66, device='cuda', generator=g)
+    fwd = M.GraphedForward(model, vis, aud)
+    with torch.no_grad():
+        _, eager = model(vis, aud)
+    assert torch.equal(fwd(vis, aud), eager)
+    vis2 = (torch.rand(B, S, 16, 3, 224, 224, device='cuda', generator=g) * 2 - 1).half()
+    with torch.no_grad():
+        _, eager2 = model(vis2, aud)
+    assert torch.equal(fwd(vis2, aud), eager2) and not torch.equal(eager, eager2)
+    with pytest.raises(ValueError):
+        fwd(vis[:, :7], aud[:, :7])
+
+    def timed(fn, n=10):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+
+    def eager_call():
+        with torch.no_grad():
+            model(vis, aud)
+    print('B=1 S=14 latency: eager launches %.2f ms, CUDA graph %.2f ms' % (timed(eager_call), timed(lambda: fwd(vis, aud))))
