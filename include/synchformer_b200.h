@@ -90,8 +90,22 @@ typedef struct sfb_attn_desc {
     int32_t n_outer, n_inner, n_heads, head_dim, Lq, Lk;
     float scale;
     int32_t impl; /* 0 = auto (specialised kernels), 1 = generic CUDA-core kernel (bring-up cross-check) */
+    /* Optional fused extra query (the Motionformer CLS query, vit_helper.py:124, which attends to ALL keys of its segment):
+     * one more query row per (outer, head) at  q_extra + o*q_extra_outer + h*head_dim  rides along with every inner problem of
+     * that outer index; its softmax state over that problem's keys (the prefix key is counted for inner == 0 only) goes to
+     *   extra_partial[((o*n_heads + h)*n_inner + i)*(head_dim + 2)] = { max (log2 units), sum, out[head_dim] / sum }   (fp32)
+     * and sfb_attention_merge_partials() combines the n_inner states.  NULL = off.  Supported where
+     * sfb_attention_extra_supported() says so (the tcgen05 space-attention kernel). */
+    const void *q_extra;
+    int64_t q_extra_outer;
+    float *extra_partial;
 } sfb_attn_desc;
 int sfb_attention(const sfb_attn_desc *desc, void *stream);
+/* 1 if sfb_attention(desc) would honour q_extra / extra_partial for this descriptor, 0 otherwise (host-only, no launch) */
+int sfb_attention_extra_supported(const sfb_attn_desc *desc);
+/* out[o*out_outer + h*head_dim + d] (bf16) = sum_i w_i partial_out_i[d] / sum_i w_i,  w_i = sum_i * 2^(max_i - max) */
+int sfb_attention_merge_partials(const float *partial, void *out, int64_t out_outer, int n_outer, int n_inner, int n_heads, int head_dim,
+                                 void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K2 — PatchEmbed3D as im2col + GEMM (vit_helper.py:436-445).  vis is (n_seg, 16, 3, 224, 224) in the layout

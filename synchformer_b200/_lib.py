@@ -25,6 +25,7 @@ class AttnDesc(Structure):
         ('Lq', c_int32), ('Lk', c_int32),
         ('scale', c_float),
         ('impl', c_int32),
+        ('q_extra', c_void_p), ('q_extra_outer', c_int64), ('extra_partial', c_void_p),
     ]
 
 
@@ -38,6 +39,8 @@ SIGNATURES = {
     'sfb_layernorm': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float,
                               c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
     'sfb_attention': (c_int, [POINTER(AttnDesc), c_void_p]),
+    'sfb_attention_extra_supported': (c_int, [POINTER(AttnDesc)]),
+    'sfb_attention_merge_partials': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     'sfb_im2col_video': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     'sfb_video_tokens': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'sfb_im2col_ast': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

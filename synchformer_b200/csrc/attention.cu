@@ -572,6 +572,53 @@ __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) 
 }  // namespace attn
 }  // namespace sfb
 
+namespace sfb {
+namespace attn {
+__global__ void __launch_bounds__(64) merge_partials_kernel(const float *__restrict__ partial, __nv_bfloat16 *__restrict__ out, int64_t out_outer,
+                                                            int n_inner, int n_heads, int hd) {
+    const int h = blockIdx.x % n_heads, o = blockIdx.x / n_heads, d = threadIdx.x;
+    if (d >= hd) return;
+    const float *p = partial + static_cast<int64_t>(blockIdx.x) * n_inner * (hd + 2);
+    float M = -INFINITY;
+    for (int i = 0; i < n_inner; ++i) M = fmaxf(M, p[i * (hd + 2)]);
+    float L = 0.f, acc = 0.f;
+    for (int i = 0; i < n_inner; ++i) {
+        const float w = p[i * (hd + 2) + 1] * exp2f(p[i * (hd + 2)] - M);
+        L += w;
+        acc = fmaf(w, p[i * (hd + 2) + 2 + d], acc);
+    }
+    out[o * out_outer + h * hd + d] = __float2bfloat16_rn(acc / L);
+}
+}  // namespace attn
+}  // namespace sfb
+
+static bool sfb_attn_aligned16(const sfb_attn_desc *d) {
+    return ((reinterpret_cast<uintptr_t>(d->q) | reinterpret_cast<uintptr_t>(d->k) | reinterpret_cast<uintptr_t>(d->v) | reinterpret_cast<uintptr_t>(d->out) |
+             reinterpret_cast<uintptr_t>(d->k_prefix) | reinterpret_cast<uintptr_t>(d->v_prefix)) & 15) == 0 &&
+           ((d->q_outer | d->q_inner | d->q_row | d->kv_outer | d->kv_inner | d->kv_row | d->o_outer | d->o_inner | d->o_row | d->prefix_outer) % 8) == 0;
+}
+
+extern "C" int sfb_attention_extra_supported(const sfb_attn_desc *desc) {
+    using namespace sfb::attn;
+    if (desc == nullptr || desc->impl != 0 || desc->head_dim != 64 || !sfb_attn_aligned16(desc)) return 0;
+    if (getenv("SFB_ATTN_TC") && atoi(getenv("SFB_ATTN_TC")) == 0) return 0;
+    if (getenv("SFB_ATTN_TC_VARIANT") && atoi(getenv("SFB_ATTN_TC_VARIANT")) != 1) return 0;
+    if ((reinterpret_cast<uintptr_t>(desc->q_extra) & 15) != 0 || desc->q_extra_outer % 8 != 0) return 0;
+    Desc d = {};
+    d.Lq = desc->Lq, d.Lk = desc->Lk, d.has_prefix = desc->k_prefix != nullptr;
+    return tc_supported(d) && desc->Lq < 256 ? 1 : 0;     // the extra query occupies query row Lq of the second 128-row tile
+}
+
+extern "C" int sfb_attention_merge_partials(const float *partial, void *out, int64_t out_outer, int n_outer, int n_inner, int n_heads, int head_dim,
+                                            void *stream) {
+    using namespace sfb;
+    SFB_CHECK_ARG(partial && out && n_outer > 0 && n_inner > 0 && n_heads > 0 && head_dim > 0 && head_dim <= 64, "sfb_attention_merge_partials: bad arguments");
+    attn::merge_partials_kernel<<<static_cast<unsigned>(n_outer) * n_heads, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        partial, reinterpret_cast<__nv_bfloat16 *>(out), out_outer, n_inner, n_heads, head_dim);
+    SFB_CHECK_LAUNCH();
+    return SFB_OK;
+}
+
 extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
     using namespace sfb;
     using namespace sfb::attn;
@@ -593,6 +640,10 @@ extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
     d.prefix_outer = desc->prefix_outer, d.has_prefix = desc->k_prefix != nullptr ? 1 : 0;
     d.n_outer = desc->n_outer, d.n_inner = desc->n_inner, d.n_heads = desc->n_heads, d.Lq = desc->Lq, d.Lk = desc->Lk;
     d.scale = desc->scale;
+    d.xq = reinterpret_cast<const __nv_bfloat16 *>(desc->q_extra), d.xq_outer = desc->q_extra_outer, d.xpartial = desc->extra_partial;
+    SFB_CHECK_ARG((d.xq == nullptr) == (d.xpartial == nullptr), "sfb_attention: q_extra and extra_partial must be given together");
+    SFB_CHECK_ARG(d.xq == nullptr || sfb_attention_extra_supported(desc) == 1,
+                  "sfb_attention: the fused extra query is not supported for this descriptor (ask sfb_attention_extra_supported first)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int HD = desc->head_dim;
 

@@ -17,6 +17,9 @@ struct Desc {
     int has_prefix;
     int n_outer, n_inner, n_heads, Lq, Lk;
     float scale;
+    const __nv_bfloat16 *xq;      // optional extra query row per (outer, head)
+    int64_t xq_outer;
+    float *xpartial;
 };
 
 // tcgen05 / TMEM kernel for hd 64, 128 < Lq <= 256, Lk + prefix <= 256 (Motionformer space attention); attention_tc.cu

@@ -145,6 +145,9 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                             const int cc = lane & 7, r = d.Lk;
                             const uint32_t sw = r * 128 + ((cc ^ (r & 7)) << 4);
                             cp_async16((lane < 8 ? sK : sV) + sw, (lane < 8 ? d.kp : d.vp) + pre_base + cc * 8);
+                        } else if (d.xq != nullptr && lane >= 16 && lane < 24) {      // fused extra query -> query row Lq
+                            const int cc = lane & 7, r = d.Lq;
+                            cp_async16(sQ + r * 128 + ((cc ^ (r & 7)) << 4), d.xq + o * d.xq_outer + h * HD + cc * 8);
                         }
                         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
                         fence_proxy_async_smem();
@@ -157,6 +160,10 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     for (int c = ptid; c < d.Lq * 8; c += kProducerWarps * 32) {
                         const int r = c >> 3, cc = c & 7;
                         cp_async16(sQ + r * 128 + ((cc ^ (r & 7)) << 4), qg + static_cast<int64_t>(r) * d.q_row + cc * 8);
+                    }
+                    if (d.xq != nullptr && ptid < 8) {
+                        const int r = d.Lq;
+                        cp_async16(sQ + r * 128 + ((ptid ^ (r & 7)) << 4), d.xq + o * d.xq_outer + h * HD + ptid * 8);
                     }
                     const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD;
                     for (int c = ptid; c < Lkp * 8; c += kProducerWarps * 32) {
@@ -213,13 +220,18 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + t * TILE_COLS;
         const float sl2 = d.scale * 1.4426950408889634f;
         const bool tile_live = t < n_tiles;
-        const bool rows_live = t * 128 + (warp & 3) * 32 < d.Lq;    // warp-uniform: a warp whose 32 rows are all padding only keeps the barriers in step
+        const int Lq_eff = d.Lq + (d.xq != nullptr ? 1 : 0);        // the fused extra query sits in query row Lq
+        const bool rows_live = t * 128 + (warp & 3) * 32 < Lq_eff;  // warp-uniform: a warp whose 32 rows are all padding only keeps the barriers in step
+        const bool is_x = d.xq != nullptr && row == d.Lq;
         int it = 0;
         for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
             if (!tile_live) continue;
+            const int ph = prob % d.n_heads, pi = (prob / d.n_heads) % d.n_inner, po = prob / (d.n_heads * d.n_inner);
+            // keys this row may see: all Lk (+ prefix); the extra query counts the prefix key in inner problem 0 only
+            const int lk = (is_x && pi != 0) ? d.Lk : Lkp;
             mbar_wait(s_bar(t), it & 1);
             tc_fence_after();
-            float inv = 0.f;
+            float inv = 0.f, mxs_keep = 0.f, sum_keep = 1.f;
             if (rows_live) {
                 uint32_t ra[32], rb[32];
                 // ---- pass 1: row maximum.  Columns 0..191 in six x32 loads (next load in flight while this one is reduced), then 192..207
@@ -229,22 +241,22 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 6; c += 2) {
                     tmem_ld32(trow + (c + 1) * 32, rb);
-                    if ((c + 1) * 32 <= Lkp) softmax_max32(ra, mx);
+                    if ((c + 1) * 32 <= d.Lk) softmax_max32(ra, mx);
                     else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (c * 32 + j < Lkp) mx = fmaxf(mx, __uint_as_float(ra[j]));
+                        for (int j = 0; j < 32; ++j) if (c * 32 + j < lk) mx = fmaxf(mx, __uint_as_float(ra[j]));
                     }
                     tmem_ld_wait_dep(rb);
                     if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
-                    if ((c + 2) * 32 <= Lkp) softmax_max32(rb, mx);
+                    if ((c + 2) * 32 <= d.Lk) softmax_max32(rb, mx);
                     else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if ((c + 1) * 32 + j < Lkp) mx = fmaxf(mx, __uint_as_float(rb[j]));
+                        for (int j = 0; j < 32; ++j) if ((c + 1) * 32 + j < lk) mx = fmaxf(mx, __uint_as_float(rb[j]));
                     }
                     tmem_ld_wait_dep(ra);
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) if (192 + j < Lkp) mx = fmaxf(mx, __uint_as_float(ra[j]));
+                for (int j = 0; j < 16; ++j) if (192 + j < lk) mx = fmaxf(mx, __uint_as_float(ra[j]));
                 const float mxs = mx * sl2;
                 // ---- pass 2: p = 2^(s*scale*log2e - max), row sum, P (bf16 pairs) written over the already consumed S columns
                 float sum = 0.f;
@@ -254,12 +266,12 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 6; c += 2) {
                     tmem_ld32(trow + (c + 1) * 32, rb);
-                    if ((c + 1) * 32 <= Lkp) softmax_exp32(ra, pk, sl2, mxs, sum);
+                    if ((c + 1) * 32 <= d.Lk) softmax_exp32(ra, pk, sl2, mxs, sum);
                     else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const float p0 = c * 32 + j < Lkp ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
-                            const float p1 = c * 32 + j + 1 < Lkp ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
+                            const float p0 = c * 32 + j < lk ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
+                            const float p1 = c * 32 + j + 1 < lk ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
                             sum += p0 + p1;
                             pk[j >> 1] = pack_bf16x2(p0, p1);
                         }
@@ -267,12 +279,12 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     tmem_ld_wait_dep(rb);
                     tmem_st16(trow + P_COL + c * 16, pk);
                     if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
-                    if ((c + 2) * 32 <= Lkp) softmax_exp32(rb, pk, sl2, mxs, sum);
+                    if ((c + 2) * 32 <= d.Lk) softmax_exp32(rb, pk, sl2, mxs, sum);
                     else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const float p0 = (c + 1) * 32 + j < Lkp ? ex2f(fmaf(__uint_as_float(rb[j]), sl2, -mxs)) : 0.f;
-                            const float p1 = (c + 1) * 32 + j + 1 < Lkp ? ex2f(fmaf(__uint_as_float(rb[j + 1]), sl2, -mxs)) : 0.f;
+                            const float p0 = (c + 1) * 32 + j < lk ? ex2f(fmaf(__uint_as_float(rb[j]), sl2, -mxs)) : 0.f;
+                            const float p1 = (c + 1) * 32 + j + 1 < lk ? ex2f(fmaf(__uint_as_float(rb[j + 1]), sl2, -mxs)) : 0.f;
                             sum += p0 + p1;
                             pk[j >> 1] = pack_bf16x2(p0, p1);
                         }
@@ -284,8 +296,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     uint32_t pt[8];
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
-                        const float p0 = 192 + j < Lkp ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
-                        const float p1 = 192 + j + 1 < Lkp ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
+                        const float p0 = 192 + j < lk ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
+                        const float p1 = 192 + j + 1 < lk ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
                         sum += p0 + p1;
                         pt[j >> 1] = pack_bf16x2(p0, p1);
                     }
@@ -293,6 +305,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 }
                 tmem_st_wait();
                 inv = 1.0f / sum;
+                mxs_keep = mxs, sum_keep = sum;
             }
             tc_fence_before();
             __syncwarp();
@@ -309,10 +322,13 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(free_bar(t));                // TMEM columns of tile t may be overwritten by the next problem
-            if (rows_live && row < d.Lq) {
-                const int h = prob % d.n_heads;
-                const int i = (prob / d.n_heads) % d.n_inner;
-                const int o = prob / (d.n_heads * d.n_inner);
+            if (is_x) {       // softmax state of the extra query over this problem's keys (sfb_attention_merge_partials combines them)
+                float *xp = d.xpartial + ((static_cast<int64_t>(po) * d.n_heads + ph) * d.n_inner + pi) * (HD + 2);
+                xp[0] = mxs_keep, xp[1] = sum_keep;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) xp[2 + k] = __uint_as_float(o0[k]) * inv, xp[34 + k] = __uint_as_float(o1[k]) * inv;
+            } else if (rows_live && row < d.Lq) {
+                const int h = ph, i = pi, o = po;
                 uint4 *og = reinterpret_cast<uint4 *>(d.out + o * d.o_outer + i * d.o_inner + static_cast<int64_t>(row) * d.o_row + h * HD);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -565,7 +581,7 @@ int launch_tc(const Desc &d, cudaStream_t st) {
         use_tma = 1;
     }
     static const int variant = getenv("SFB_ATTN_TC_VARIANT") ? atoi(getenv("SFB_ATTN_TC_VARIANT")) : 1;   // 1 = persistent (default: measured 2.2 vs 3.0 ms), 2 = two CTAs per SM
-    if (use_tma && variant == 2) {
+    if (use_tma && variant == 2 && d.xq == nullptr) {
         static bool attr2 = false;
         if (!attr2) {
             SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC2));

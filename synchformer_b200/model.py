@@ -164,18 +164,19 @@ class MotionFormer(_KernelModule):
         """DividedAttention.forward vit_helper.py:100-158 on the fused (n*1569, 2304) qkv activations."""
         row, seg = 3 * D, V_TOK * 3 * D
         q, k, v = qkv, qkv[:, D:], qkv[:, 2 * D:]
-        # CLS query attends to all 1569 keys (:124)
-        ops.attention(q, k, v, att, q_strides=(seg, 0, row), kv_strides=(seg, 0, row), o_strides=(V_TOK * D, 0, D), n_outer=n, n_inner=1,
-                      n_heads=12, head_dim=64, Lq=1, Lk=V_TOK, scale=0.125)
         q1, k1, v1, o1 = qkv[1:], qkv[1:, D:], qkv[1:, 2 * D:], att[1:]
         if mode == 'time':    # '(b n) f d': 8 frames of one location + CLS key/value
-            ops.attention(q1, k1, v1, o1, q_strides=(seg, row, V_SPACE * row), kv_strides=(seg, row, V_SPACE * row),
-                          o_strides=(V_TOK * D, D, V_SPACE * D), n_outer=n, n_inner=V_SPACE, n_heads=12, head_dim=64, Lq=V_FRAMES, Lk=V_FRAMES,
-                          scale=0.125, k_prefix=k, v_prefix=v, prefix_outer=seg)
-        else:                 # '(b f) n d': 196 locations of one frame + CLS key/value
-            ops.attention(q1, k1, v1, o1, q_strides=(seg, V_SPACE * row, row), kv_strides=(seg, V_SPACE * row, row),
-                          o_strides=(V_TOK * D, V_SPACE * D, D), n_outer=n, n_inner=V_FRAMES, n_heads=12, head_dim=64, Lq=V_SPACE, Lk=V_SPACE,
-                          scale=0.125, k_prefix=k, v_prefix=v, prefix_outer=seg)
+            fused = ops.attention(q1, k1, v1, o1, q_strides=(seg, row, V_SPACE * row), kv_strides=(seg, row, V_SPACE * row),
+                                  o_strides=(V_TOK * D, D, V_SPACE * D), n_outer=n, n_inner=V_SPACE, n_heads=12, head_dim=64, Lq=V_FRAMES,
+                                  Lk=V_FRAMES, scale=0.125, k_prefix=k, v_prefix=v, prefix_outer=seg)
+        else:                 # '(b f) n d': 196 locations of one frame + CLS key/value; the CLS query rides along (fused) when supported
+            fused = ops.attention(q1, k1, v1, o1, q_strides=(seg, V_SPACE * row, row), kv_strides=(seg, V_SPACE * row, row),
+                                  o_strides=(V_TOK * D, V_SPACE * D, D), n_outer=n, n_inner=V_FRAMES, n_heads=12, head_dim=64, Lq=V_SPACE,
+                                  Lk=V_SPACE, scale=0.125, k_prefix=k, v_prefix=v, prefix_outer=seg,
+                                  q_extra=q, q_extra_outer=seg, extra_out=att, extra_out_outer=V_TOK * D)
+        if not fused:         # CLS query attends to all 1569 keys (:124)
+            ops.attention(q, k, v, att, q_strides=(seg, 0, row), kv_strides=(seg, 0, row), o_strides=(V_TOK * D, 0, D), n_outer=n, n_inner=1,
+                          n_heads=12, head_dim=64, Lq=1, Lk=V_TOK, scale=0.125)
 
     def _encode_chunk(self, vis: torch.Tensor, P, W) -> torch.Tensor:
         """vis (n, 16, 3, 224, 224) -> (n, 8, 768) fp32."""

@@ -99,9 +99,16 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, q_strides, kv_strides, o_strides, n_outer: int,
               n_inner: int, n_heads: int, head_dim: int, Lq: int, Lk: int, scale: float, k_prefix: Optional[torch.Tensor] = None,
-              v_prefix: Optional[torch.Tensor] = None, prefix_outer: int = 0, impl: Optional[int] = None):
+              v_prefix: Optional[torch.Tensor] = None, prefix_outer: int = 0, impl: Optional[int] = None,
+              q_extra: Optional[torch.Tensor] = None, q_extra_outer: int = 0, extra_out: Optional[torch.Tensor] = None,
+              extra_out_outer: int = 0) -> bool:
     """softmax(scale q k^T) v on strided bf16 views; q/k/v/out are tensors whose data_ptr() is the address of problem
-    (0, 0), head 0, row 0; *_strides = (outer, inner, row) in elements.  See sfb_attn_desc in the header."""
+    (0, 0), head 0, row 0; *_strides = (outer, inner, row) in elements.  See sfb_attn_desc in the header.
+
+    q_extra / extra_out: ask for the fused extra query (one more query row per (outer, head) that attends to the keys of ALL inner
+    problems of its outer index, e.g. the Motionformer CLS query); its merged result goes to extra_out + o*extra_out_outer + h*head_dim.
+    Returns True if the extra query was fused; False if this descriptor does not support it (then only the regular rows were computed
+    and the caller runs the extra query as its own attention call)."""
     require_cuda(q, 'q')
     for t in (q, k, v, out):
         assert t.dtype == torch.bfloat16
@@ -116,8 +123,25 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     d.n_outer, d.n_inner, d.n_heads, d.head_dim, d.Lq, d.Lk = n_outer, n_inner, n_heads, head_dim, Lq, Lk
     d.scale = scale
     d.impl = ATTN_IMPL if impl is None else impl
-    check(_lib.load().sfb_attention(ctypes.byref(d), _stream(q)), 'sfb_attention')
+    d.q_extra, d.q_extra_outer, d.extra_partial = None, 0, None
+    lib = _lib.load()
+    fused, partial = False, None
+    if q_extra is not None:
+        assert extra_out is not None and q_extra.dtype == torch.bfloat16 and extra_out.dtype == torch.bfloat16
+        d.q_extra, d.q_extra_outer = q_extra.data_ptr(), q_extra_outer
+        if lib.sfb_attention_extra_supported(ctypes.byref(d)) == 1:
+            partial = torch.empty((n_outer * n_heads * n_inner, head_dim + 2), device=q.device, dtype=torch.float32)
+            d.extra_partial = partial.data_ptr()
+            fused = True
+        else:
+            d.q_extra, d.q_extra_outer = None, 0
+    check(lib.sfb_attention(ctypes.byref(d), _stream(q)), 'sfb_attention')
     _count()
+    if fused:
+        check(lib.sfb_attention_merge_partials(_p(partial), _p(extra_out), extra_out_outer, n_outer, n_inner, n_heads, head_dim, _stream(q)),
+              'sfb_attention_merge_partials')
+        _count()
+    return fused
 
 
 _VIDEO_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.uint8: 3}

@@ -317,3 +317,31 @@ def test_mel_frontend_against_oracle_and_reference_golden(cuda_device, golden_di
     g = torch.Generator().manual_seed(9)
     noise = torch.randn(5, 10240, generator=g) * 0.3
     assert (ops.mel_frontend(noise.cuda()).cpu() - O.mel_frontend(noise).float()).abs().max() < 5e-4
+
+
+def test_space_attention_with_fused_cls_query(cuda_device):
+    """The CLS query (vit_helper.py:124: one query against all 1569 keys of its segment) rides along with the 8 per-frame space-attention
+    problems of the tcgen05 kernel and is merged from their partial softmax states; result must equal the stand-alone computation."""
+    from synchformer_b200 import ops
+    n, D = 3, 768
+    g = torch.Generator(device='cuda').manual_seed(23)
+    qkv = _bf(torch.randn(n * 1569, 3 * D, device='cuda', generator=g))
+    att = torch.zeros(n * 1569, D, device='cuda', dtype=torch.bfloat16)
+    row, seg = 3 * D, 1569 * 3 * D
+    fused = ops.attention(qkv[1:], qkv[1:, D:], qkv[1:, 2 * D:], att[1:], q_strides=(seg, 196 * row, row), kv_strides=(seg, 196 * row, row),
+                          o_strides=(1569 * D, 196 * D, D), n_outer=n, n_inner=8, n_heads=12, head_dim=64, Lq=196, Lk=196, scale=0.125,
+                          k_prefix=qkv[:, D:], v_prefix=qkv[:, 2 * D:], prefix_outer=seg,
+                          q_extra=qkv, q_extra_outer=seg, extra_out=att, extra_out_outer=1569 * D)
+    assert fused, 'the tcgen05 space-attention kernel should take the extra query'
+    t = qkv.float().view(n, 1569, 3, 12, 64)
+    q, k, v = t[:, :, 0].permute(0, 2, 1, 3), t[:, :, 1].permute(0, 2, 1, 3), t[:, :, 2].permute(0, 2, 1, 3)
+    ref_cls = _ref_attention(q[:, :, :1], k, v, 0.125)                       # (n, h, 1, 64)
+    got_cls = att.view(n, 1569, 12, 64)[:, :1].permute(0, 2, 1, 3).float()
+    torch.cuda.synchronize()
+    assert rel_l2(got_cls, ref_cls) < 6e-3
+    # and the regular rows are unchanged by the extra row
+    att2 = torch.zeros_like(att)
+    ops.attention(qkv[1:], qkv[1:, D:], qkv[1:, 2 * D:], att2[1:], q_strides=(seg, 196 * row, row), kv_strides=(seg, 196 * row, row),
+                  o_strides=(1569 * D, 196 * D, D), n_outer=n, n_inner=8, n_heads=12, head_dim=64, Lq=196, Lk=196, scale=0.125,
+                  k_prefix=qkv[:, D:], v_prefix=qkv[:, 2 * D:], prefix_outer=seg)
+    assert torch.equal(att.view(n, 1569, D)[:, 1:], att2.view(n, 1569, D)[:, 1:])
