@@ -113,6 +113,11 @@ int sfb_attention_merge_partials(const float *partial, void *out, int64_t out_ou
  * in_dtype: 0 fp32, 1 fp16, 2 bf16, 3 uint8 (uint8 fuses RGBToHalfToZeroOne + RGBNormalize(.5,.5),
  * dataset/transforms.py:647-669).  A is (n_seg*1568, 1536) bf16, K order (c, dt, dy, dx) = Conv3d weight order. */
 int sfb_im2col_video(const void *vis, int in_dtype, void *A, int n_seg, void *stream);
+/* N2: segment slicing fused into the gather - GenerateMultipleSegments (dataset/transforms.py:402-499) on the device.
+ * clip is (n_clips, n_frames, 3, 224, 224); segment s of clip b covers frames [v_start + s*v_stride, +16); A is
+ * (n_clips*n_segments*1568, 1536).  Overlapping segments (stride 8) are no longer shipped twice over PCIe. */
+int sfb_im2col_video_clip(const void *clip, int in_dtype, void *A, int n_clips, int n_frames, int n_segments, int v_start, int v_stride,
+                          void *stream);
 /* + bias already added by the GEMM; adds pos_embed[1+n] + temp_embed[f], prepends cls_token + pos_embed[0]
  * (video_model_builder.py:221-254).  patch (n_seg*1568, 768) fp32 -> x (n_seg, 1569, 768) fp32 */
 int sfb_video_tokens(const float *patch, const float *cls_token, const float *pos_embed, const float *temp_embed, float *x,
@@ -142,6 +147,9 @@ int sfb_cast_f32_bf16(const float *in, void *out, int64_t n, void *stream);
  * wave (n_seg, 10240) fp32 -> out (n_seg, 128, 66) fp32.  The first call uploads three constant tables
  * (twiddles, window, filterbank) to static device arrays with a synchronous copy. */
 int sfb_mel_frontend(const float *wave, float *out, int n_seg, void *stream);
+/* same on un-duplicated waveforms: wave (n_clips, clip_stride samples); segment s of clip b = samples [a_start + s*a_stride, +10240) */
+int sfb_mel_frontend_clip(const float *wave, int64_t clip_stride, float *out, int n_clips, int n_segments, int a_start, int a_stride,
+                          void *stream);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,7 @@ SIGNATURES = {
     'sfb_attention_extra_supported': (c_int, [POINTER(AttnDesc)]),
     'sfb_attention_merge_partials': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     'sfb_im2col_video': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    'sfb_im2col_video_clip': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'sfb_video_tokens': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'sfb_im2col_ast': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'sfb_ast_tokens': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
@@ -51,6 +52,7 @@ SIGNATURES = {
                               c_int, c_int, c_void_p]),
     'sfb_cast_f32_bf16': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     'sfb_mel_frontend': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    'sfb_mel_frontend_clip': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -40,8 +40,12 @@ __device__ __forceinline__ void load8(const void *base, int64_t idx, float *f) {
     }
 }
 
+// n_segments == 0: `vis` already holds one 16-frame block per segment (idx is the input chunk index).  n_segments > 0 (N2, segment
+// slicing fused into the gather, dataset/transforms.py:402-499): `vis` is (n_clips, n_frames, 3, 224, 224) and segment s of clip b
+// covers frames [v_start + s * v_stride, + 16) - overlapping segments re-read shared frames from HBM/L2 instead of from the host.
 template <int DT>
-__global__ void __launch_bounds__(256) im2col_video_kernel(const void *__restrict__ vis, __nv_bfloat16 *__restrict__ A, int64_t n_chunks) {
+__global__ void __launch_bounds__(256) im2col_video_kernel(const void *__restrict__ vis, __nv_bfloat16 *__restrict__ A, int64_t n_chunks,
+                                                           int n_frames, int n_segments, int v_start, int v_stride) {
     const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
     if (idx >= n_chunks) return;
     const int X8 = static_cast<int>(idx % 28);
@@ -53,7 +57,12 @@ __global__ void __launch_bounds__(256) im2col_video_kernel(const void *__restric
     const int t = static_cast<int>(r % 16);
     const int64_t seg = r / 16;
     float f[8];
-    load8<DT>(vis, idx, f);
+    int64_t in_idx = idx;
+    if (n_segments > 0) {
+        const int64_t frame = (seg / n_segments) * n_frames + v_start + (seg % n_segments) * v_stride + t;
+        in_idx = ((frame * 3 + c) * 224 + Y) * 28 + X8;
+    }
+    load8<DT>(vis, in_idx, f);
     const int64_t row = seg * 1568 + (t >> 1) * 196 + (Y >> 4) * 14 + (X8 >> 1);
     const int col = c * 512 + (t & 1) * 256 + (Y & 15) * 16 + (X8 & 1) * 8;
     uint4 u;
@@ -209,23 +218,39 @@ static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) 
 
 }  // namespace sfb
 
-extern "C" int sfb_im2col_video(const void *vis, int in_dtype, void *A, int n_seg, void *stream) {
+static int im2col_video_launch(const void *vis, int in_dtype, void *A, int64_t n_seg, int n_frames, int n_segments, int v_start, int v_stride,
+                               cudaStream_t st) {
     using namespace sfb;
-    SFB_CHECK_ARG(vis && A && n_seg > 0, "sfb_im2col_video: bad arguments");
-    SFB_CHECK_ARG(al16(vis) && al16(A), "sfb_im2col_video: pointers must be 16-byte aligned");
-    const int64_t n_chunks = static_cast<int64_t>(n_seg) * 16 * 3 * 224 * 28;
+    const int64_t n_chunks = n_seg * 16 * 3 * 224 * 28;
     SFB_CHECK_ARG(blocks_for(n_chunks) < (1u << 31), "sfb_im2col_video: too many segments for one launch");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     __nv_bfloat16 *a = reinterpret_cast<__nv_bfloat16 *>(A);
     switch (in_dtype) {
-        case 0: im2col_video_kernel<0><<<blocks_for(n_chunks), 256, 0, st>>>(vis, a, n_chunks); break;
-        case 1: im2col_video_kernel<1><<<blocks_for(n_chunks), 256, 0, st>>>(vis, a, n_chunks); break;
-        case 2: im2col_video_kernel<2><<<blocks_for(n_chunks), 256, 0, st>>>(vis, a, n_chunks); break;
-        case 3: im2col_video_kernel<3><<<blocks_for(n_chunks), 256, 0, st>>>(vis, a, n_chunks); break;
+        case 0: im2col_video_kernel<0><<<blocks_for(n_chunks), 256, 0, st>>>(vis, a, n_chunks, n_frames, n_segments, v_start, v_stride); break;
+        case 1: im2col_video_kernel<1><<<blocks_for(n_chunks), 256, 0, st>>>(vis, a, n_chunks, n_frames, n_segments, v_start, v_stride); break;
+        case 2: im2col_video_kernel<2><<<blocks_for(n_chunks), 256, 0, st>>>(vis, a, n_chunks, n_frames, n_segments, v_start, v_stride); break;
+        case 3: im2col_video_kernel<3><<<blocks_for(n_chunks), 256, 0, st>>>(vis, a, n_chunks, n_frames, n_segments, v_start, v_stride); break;
         default: set_error("sfb_im2col_video: in_dtype %d not in {0 f32, 1 f16, 2 bf16, 3 u8}", in_dtype); return SFB_E_INVALID;
     }
     SFB_CHECK_LAUNCH();
     return SFB_OK;
+}
+
+extern "C" int sfb_im2col_video(const void *vis, int in_dtype, void *A, int n_seg, void *stream) {
+    using namespace sfb;
+    SFB_CHECK_ARG(vis && A && n_seg > 0, "sfb_im2col_video: bad arguments");
+    SFB_CHECK_ARG(al16(vis) && al16(A), "sfb_im2col_video: pointers must be 16-byte aligned");
+    return im2col_video_launch(vis, in_dtype, A, n_seg, 0, 0, 0, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sfb_im2col_video_clip(const void *clip, int in_dtype, void *A, int n_clips, int n_frames, int n_segments, int v_start,
+                                     int v_stride, void *stream) {
+    using namespace sfb;
+    SFB_CHECK_ARG(clip && A && n_clips > 0 && n_frames > 0 && n_segments > 0 && v_start >= 0 && v_stride > 0, "sfb_im2col_video_clip: bad arguments");
+    SFB_CHECK_ARG(v_start + (n_segments - 1) * v_stride + 16 <= n_frames, "sfb_im2col_video_clip: %d segments of 16 frames (start %d, stride %d) do not fit in %d frames",
+                  n_segments, v_start, v_stride, n_frames);
+    SFB_CHECK_ARG(al16(clip) && al16(A), "sfb_im2col_video_clip: pointers must be 16-byte aligned");
+    return im2col_video_launch(clip, in_dtype, A, static_cast<int64_t>(n_clips) * n_segments, n_frames, n_segments, v_start, v_stride,
+                               reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sfb_video_tokens(const float *patch, const float *cls_token, const float *pos_embed, const float *temp_embed, float *x,

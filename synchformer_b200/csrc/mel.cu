@@ -28,7 +28,8 @@ __device__ float g_fb[N_FREQ * N_MEL];     // [freq][mel]
 // X[512-k] = (Ae - Ao) + i (Be - Bo).  Threads 0..256 own the pairs (k, 512 - k).
 constexpr int MEL_THREADS = 288;
 
-__global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float *__restrict__ wave, float *__restrict__ out) {
+__global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float *__restrict__ wave, float *__restrict__ out, int n_segments,
+                                                          int64_t clip_stride, int a_start, int a_stride) {
     __shared__ double2 tw[N_FFT];
     __shared__ float xs[WIN];
     __shared__ float pw[N_FREQ + 3];
@@ -36,7 +37,8 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float *__restric
     const int64_t seg = blockIdx.x / N_FRAMES;
     const int tid = threadIdx.x;
     for (int j = tid; j < N_FFT; j += MEL_THREADS) tw[j] = g_twiddle[j];
-    const float *w = wave + seg * SEG;
+    // segment `seg` = segment (seg % n_segments) of clip (seg / n_segments): windows may overlap inside one un-duplicated waveform
+    const float *w = wave + (seg / n_segments) * clip_stride + a_start + (seg % n_segments) * static_cast<int64_t>(a_stride);
     for (int n = tid; n < WIN; n += MEL_THREADS) {
         int idx = frame * HOP + WIN_OFF + n - N_FFT / 2;          // index into the un-padded segment
         idx = idx < 0 ? -idx : (idx >= SEG ? 2 * (SEG - 1) - idx : idx);   // reflect padding (torch.stft center=True)
@@ -109,7 +111,21 @@ extern "C" int sfb_mel_frontend(const float *wave, float *out, int n_seg, void *
     SFB_CHECK_ARG(wave && out && n_seg > 0, "sfb_mel_frontend: bad arguments");
     int rc = init_tables();   // first call only: three small host->device table uploads
     if (rc != SFB_OK) return rc;
-    mel_kernel<<<static_cast<unsigned>(static_cast<int64_t>(n_seg) * N_FRAMES), MEL_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wave, out);
+    mel_kernel<<<static_cast<unsigned>(static_cast<int64_t>(n_seg) * N_FRAMES), MEL_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wave, out, 1, SEG, 0, 0);
+    SFB_CHECK_LAUNCH();
+    return SFB_OK;
+}
+
+extern "C" int sfb_mel_frontend_clip(const float *wave, int64_t clip_stride, float *out, int n_clips, int n_segments, int a_start, int a_stride,
+                                     void *stream) {
+    using namespace sfb;
+    using namespace sfb::mel;
+    SFB_CHECK_ARG(wave && out && n_clips > 0 && n_segments > 0 && a_start >= 0 && a_stride > 0, "sfb_mel_frontend_clip: bad arguments");
+    SFB_CHECK_ARG(a_start + static_cast<int64_t>(n_segments - 1) * a_stride + SEG <= clip_stride, "sfb_mel_frontend_clip: segments do not fit in the waveform");
+    int rc = init_tables();
+    if (rc != SFB_OK) return rc;
+    mel_kernel<<<static_cast<unsigned>(static_cast<int64_t>(n_clips) * n_segments * N_FRAMES), MEL_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        wave, out, n_segments, clip_stride, a_start, a_stride);
     SFB_CHECK_LAUNCH();
     return SFB_OK;
 }

@@ -178,11 +178,12 @@ class MotionFormer(_KernelModule):
             ops.attention(q, k, v, att, q_strides=(seg, 0, row), kv_strides=(seg, 0, row), o_strides=(V_TOK * D, 0, D), n_outer=n, n_inner=1,
                           n_heads=12, head_dim=64, Lq=1, Lk=V_TOK, scale=0.125)
 
-    def _encode_chunk(self, vis: torch.Tensor, P, W) -> torch.Tensor:
-        """vis (n, 16, 3, 224, 224) -> (n, 8, 768) fp32."""
-        n = vis.shape[0]
-        dev = vis.device
-        a = ops.im2col_video(vis)
+    def _encode_chunk(self, vis: Optional[torch.Tensor], P, W, a: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """vis (n, 16, 3, 224, 224) [or its im2col matrix `a` (n*1568, 1536)] -> (n, 8, 768) fp32."""
+        if a is None:
+            a = ops.im2col_video(vis)
+        n = a.shape[0] // 1568
+        dev = a.device
         patch = ops.gemm(a, W['pe_w'], P['patch_embed_3d.proj.bias'], out_f32=True)
         x = ops.video_tokens(patch, P['cls_token'], P['pos_embed'], P['temp_embed'], n)           # (n*1569, 768) fp32 residual stream
         del a, patch
@@ -217,6 +218,18 @@ class MotionFormer(_KernelModule):
         if cont_mask is not None:
             raise NotImplementedError('cont_mask is not supported (no caller in the reference passes it)')
         return self.encode(x.permute(0, 1, 3, 2, 4, 5)), None
+
+    def encode_clip(self, clip: torch.Tensor, n_segments: int, v_start: int, v_stride: int) -> torch.Tensor:
+        """N2: clip (B, n_frames, 3, 224, 224), any supported dtype incl. raw uint8 -> (B, S, 8, 768); the S overlapping 16-frame
+        segments (GenerateMultipleSegments, dataset/transforms.py:402-499) are sliced inside the patch-embedding gather."""
+        ops.require_cuda(clip, 'clip')
+        B = clip.shape[0]
+        P, W = self.weights()
+        per = max(1, self.max_segments_per_pass // n_segments)               # whole clips per pass
+        outs = [self._encode_chunk(None, P, W, a=ops.im2col_video_clip(clip[b:b + per].contiguous(), n_segments, v_start, v_stride))
+                for b in range(0, B, per)]
+        feats = (outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)).view(B, n_segments, V_FRAMES, D)
+        return feats.mean(dim=2) if self.time_pool else feats
 
     def encode(self, vis: torch.Tensor) -> torch.Tensor:
         """vis (B, S, T=16, C=3, 224, 224) fp32 / fp16 / bf16 / uint8 -> (B, S, 8, 768) fp32."""
@@ -465,6 +478,33 @@ class Synchformer(nn.Module):
         logits = self.transformer(v, a)
         loss = self.compute_loss(logits, targets, loss_fn)
         return loss, logits
+
+    @staticmethod
+    def segment_ranges(n_vframes: int, n_aframes: int, n_segments: int, segment_size_vframes: int = 16, step_size_seg: float = 0.5,
+                       v_fps: int = 25, a_fps: int = 16000):
+        """(v_start, v_stride, a_start, a_stride) of GenerateMultipleSegments with is_start_random=False
+        (dataset/transforms.py:421-499; configs/sync.yaml:93-101, 170-176): the segment sequence is centred in the clip."""
+        seg_a = int(segment_size_vframes / v_fps * a_fps)
+        v_stride, a_stride = int(step_size_seg * segment_size_vframes), int(step_size_seg * seg_a)
+        seq = n_segments * step_size_seg + (1 - step_size_seg)
+        v_len = int(seq * segment_size_vframes)
+        if v_len > n_vframes or int(seq * seg_a) > n_aframes:
+            raise ValueError(f'cant make {n_segments} segs of len {segment_size_vframes} in a vid of len {n_vframes}')
+        v_start = (n_vframes - v_len) // 2
+        a_start = int(v_start / v_fps * a_fps)
+        return v_start, v_stride, a_start, a_stride
+
+    @torch.no_grad()
+    def forward_clip(self, frames: torch.Tensor, waveform: torch.Tensor, n_segments: int = 14, **seg_kwargs) -> torch.Tensor:
+        """un-segmented inputs straight from the decoder - frames (B, n_frames, 3, 224, 224) uint8 / fp16 / fp32 and
+        waveform (B, n_samples) fp32 at 16 kHz -> offset logits (B, n_cls).  Segment slicing, uint8 normalisation and the mel front-end
+        all happen inside the kernels; equivalent to the transform chain + forward() on the explicit (B, S, ...) tensors."""
+        v0, vs, a0, as_ = self.segment_ranges(frames.shape[1], waveform.shape[1], n_segments, **seg_kwargs)
+        vis = self.vfeat_extractor.encode_clip(frames, n_segments, v0, vs)
+        mel = ops.mel_frontend_clip(waveform.float().contiguous(), n_segments, a0, as_)
+        aud = self.afeat_extractor.encode(mel)
+        v, a = self.project(vis, aud)
+        return self.transformer(v, a)
 
     def extract_vfeats(self, vis, for_loop=False, vis_mask=None):
         if vis_mask is not None:

@@ -161,6 +161,20 @@ def im2col_video(vis: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
     return out
 
 
+def im2col_video_clip(clip: torch.Tensor, n_segments: int, v_start: int, v_stride: int) -> torch.Tensor:
+    """clip (n_clips, n_frames, 3, 224, 224) -> (n_clips * n_segments * 1568, 1536) bf16; segment s = frames [v_start + s*v_stride, +16)."""
+    require_cuda(clip, 'clip')
+    assert clip.is_contiguous() and clip.dim() == 5 and tuple(clip.shape[2:]) == (3, 224, 224), f'bad clip shape {tuple(clip.shape)}'
+    if clip.dtype not in _VIDEO_DTYPES:
+        raise _lib.SfbError(f'unsupported video dtype {clip.dtype}')
+    n_clips, n_frames = clip.shape[:2]
+    out = torch.empty((n_clips * n_segments * 1568, 1536), device=clip.device, dtype=torch.bfloat16)
+    check(_lib.load().sfb_im2col_video_clip(_p(clip), _VIDEO_DTYPES[clip.dtype], _p(out), n_clips, n_frames, n_segments, v_start, v_stride,
+                                            _stream(clip)), 'sfb_im2col_video_clip')
+    _count()
+    return out
+
+
 def video_tokens(patch: torch.Tensor, cls_token: torch.Tensor, pos_embed: torch.Tensor, temp_embed: torch.Tensor, n_seg: int,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if out is None:
@@ -222,5 +236,17 @@ def mel_frontend(wave: torch.Tensor) -> torch.Tensor:
     n = wave.numel() // 10240
     out = torch.empty((*wave.shape[:-1], 128, 66), device=wave.device, dtype=torch.float32)
     check(_lib.load().sfb_mel_frontend(_p(wave), _p(out), n, _stream(wave)), 'sfb_mel_frontend')
+    _count()
+    return out
+
+
+def mel_frontend_clip(wave: torch.Tensor, n_segments: int, a_start: int, a_stride: int) -> torch.Tensor:
+    """wave (n_clips, n_samples) fp32 un-duplicated waveforms -> (n_clips, n_segments, 128, 66); segment s = samples [a_start + s*a_stride, +10240)."""
+    require_cuda(wave, 'wave')
+    assert wave.dtype == torch.float32 and wave.is_contiguous() and wave.dim() == 2
+    n_clips = wave.shape[0]
+    out = torch.empty((n_clips, n_segments, 128, 66), device=wave.device, dtype=torch.float32)
+    check(_lib.load().sfb_mel_frontend_clip(_p(wave), wave.shape[1], _p(out), n_clips, n_segments, a_start, a_stride, _stream(wave)),
+          'sfb_mel_frontend_clip')
     _count()
     return out

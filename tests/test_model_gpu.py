@@ -250,3 +250,24 @@ def test_cuda_graph_replay_matches_eager_launches(cuda_device):
         with torch.no_grad():
             model(vis, aud)
     print('B=1 S=14 latency: eager launches %.2f ms, CUDA graph %.2f ms' % (timed(eager_call), timed(lambda: fwd(vis, aud))))
+
+
+def test_forward_clip_equals_explicit_segments(cuda_device):
+    """N2: raw uint8 frames of an un-segmented 125-frame clip + the un-duplicated waveform give bit-identical logits to the reference-style
+    pipeline (GenerateMultipleSegments slicing on the host, normalised fp32 video, per-segment waveforms)."""
+    from synchformer_b200 import model as M, ops, synth
+    B, S, T = 2, 14, 125
+    model = M.build_synchformer(n_segments=S, state_dict=synth.synthetic_state_dict(1337, n_segments=S), device=cuda_device)
+    g = torch.Generator().manual_seed(12)
+    frames = torch.randint(0, 256, (B, T, 3, 224, 224), generator=g, dtype=torch.uint8)
+    wave = torch.randn(B, 5 * 16000, generator=g) * 0.1
+    v0, vs, a0, a_s = model.segment_ranges(T, wave.shape[1], S)
+    assert (v0, vs, a0, a_s) == (2, 8, 1280, 5120)                      # what GenerateMultipleSegments computes for a 5 s / 25 fps clip
+    logits = model.forward_clip(frames.cuda(), wave.cuda(), n_segments=S)
+    vis = torch.stack([frames[:, v0 + s * vs: v0 + s * vs + 16] for s in range(S)], dim=1)        # (B, S, 16, 3, 224, 224) uint8
+    seg_wave = torch.stack([wave[:, a0 + s * a_s: a0 + s * a_s + 10240] for s in range(S)], dim=1).contiguous()
+    with torch.no_grad():
+        _, ref = model(vis.cuda(), ops.mel_frontend(seg_wave.cuda()).unsqueeze(2))
+    assert logits.shape == (B, 21) and torch.equal(logits, ref)
+    with pytest.raises(ValueError):
+        model.segment_ranges(100, 5 * 16000, 14)
