@@ -285,6 +285,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             };
             if (out_f32 && has_res) load_res(0);
+            // The accumulator is handed back to the MMA issuer as soon as this warp's LAST tcgen05.ld of the tile has completed - the
+            // bias / GELU / transpose / global stores that follow work on registers only.  (Releasing at the end of the epilogue, with a
+            // release-ordered remote arrive behind the global stores, showed up as ~10 % of the stall samples and kept tile i+2's
+            // main loop waiting for tile i's stores.)
+            auto release_acc = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+                }
+            };
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             if (out_f32) {
@@ -295,6 +306,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     uint32_t r[32];
                     tmem_ld32(tbase + c * 32, r);
                     tmem_ld_wait();
+                    if (c == 1) release_acc();
                     if (col0 < p.N) {          // warp-uniform
                         float v[32];
 #pragma unroll
@@ -332,12 +344,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             } else {
                 const int col0 = n0;
-                if (col0 < p.N) {              // warp-uniform
+                {
 #pragma unroll
                     for (int hseg = 0; hseg < 2; ++hseg) {
                         uint32_t r[32];
                         tmem_ld32(tbase + hseg * 32, r);
                         tmem_ld_wait();
+                        if (hseg == 1) release_acc();
+                        if (col0 >= p.N) continue;       // warp-uniform
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -361,6 +375,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                 make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
                                            pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
                     }
+                }
+                if (col0 < p.N) {
                     __syncwarp();
                     const int gcol = col0 + cc * 8;
 #pragma unroll
@@ -373,11 +389,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                     __syncwarp();
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
             }
             if (++acc == kAccStages) {
                 acc = 0;
