@@ -151,6 +151,57 @@ int sfb_mel_frontend(const float *wave, float *out, int n_seg, void *stream);
 int sfb_mel_frontend_clip(const float *wave, int64_t clip_stride, float *out, int n_clips, int n_segments, int a_start, int a_stride,
                           void *stream);
 
+/* =========================================================================================================
+ * N3 — training step of the synchronisation module: vproj / aproj + GlobalTransformer forward with dropout and
+ * backward (modules/transformer.py:31-97, sync_model.py:55-62, 150-173; driven by scripts/train_utils.py:373-386).  The linear
+ * layers' dX = dY W and dW = dY^T X reuse sfb_gemm_bf16 on operands transposed by sfb_transpose_bf16; everything else is below.
+ * ========================================================================================================= */
+
+/* nn.Dropout (transformer.py:47-48,74,92; sync_model.py:137) with a counter-based mask, forward and backward in one entry point:
+ *     out[e] = (residual ? residual[e] : 0) + in[e] * (keep(seed, site, e) ? 1 / (1 - p) : 0)         e in [0, n), n % 4 == 0
+ *     keep(seed, site, e) = Philox4x32-10(counter = (e >> 2, site, 0), key = seed)[e & 3] >= floor(p * 2^32)
+ * in / residual fp32, out fp32 (out_bf16 == 0) or bf16; out may alias in or residual.  p == 0 degenerates to a copy / cast / add.
+ * The same (seed, site, e) gives the same mask in every kernel of the library; e is the linear index into the dropped tensor. */
+int sfb_dropout(const float *in, const float *residual, void *out, int out_bf16, int64_t n, float p, uint64_t seed, uint32_t site,
+                void *stream);
+
+/* nn.GELU on the bf16 pre-activation (transformer.py:89) and its derivative: y = gelu(x); dx = dy * (Phi(x) + x phi(x)).  n % 8 == 0 */
+int sfb_gelu_fwd(const void *x, void *y, int64_t n, void *stream);
+int sfb_gelu_bwd(const void *dy, const void *x, void *dx, int64_t n, void *stream);
+
+/* out[c][r] = in[r][c] for r < R, c < C (bf16); columns R <= r < ld_out of out are zero-filled, so ld_out can be R rounded up to the
+ * multiple of 8 that sfb_gemm_bf16 needs as its K. */
+int sfb_transpose_bf16(const void *in, int64_t ld_in, int R, int C, void *out, int64_t ld_out, void *stream);
+
+/* out[c] = sum_r in[r][c]  (bias gradients; pos-emb / token gradients summed over the batch).  in is bf16 (in_bf16 != 0) or fp32,
+ * N and ld even.  Deterministic two-stage reduction through `workspace` (up to 64 * N floats are used; NULL = single stage). */
+int sfb_colsum(const void *in, int in_bf16, int64_t ld, int M, int N, float *out, float *workspace, int64_t workspace_floats, void *stream);
+
+/* nn.LayerNorm backward over D = 768 in fp32 (transformer.py:84-85, sync_model.py:126-127,143):
+ *     dx[r] (+)= rstd (g - mean(g) - xhat mean(g xhat)),  g = dy[row(r)] * gamma;   dgamma = sum_r dy xhat;   dbeta = sum_r dy
+ * dy row of output row r: (r / group) * group_stride + offset + r % group (the gather of sfb_layernorm / the token layout of
+ * sfb_sync_tokens).  accumulate != 0 adds into dx (residual branch).  dbeta must be dgamma + 768 (one (2, 768) buffer).
+ * workspace: sfb_layernorm_bwd_workspace_floats(rows) floats. */
+int sfb_layernorm_bwd_workspace_floats(int rows);
+int sfb_layernorm_bwd(const float *dy, int64_t lddy, int group, int group_stride, int offset, const float *x, int64_t ldx,
+                      const float *gamma, float eps, float *dx, int64_t lddx, int accumulate, float *dgamma, float *dbeta,
+                      float *workspace, int64_t workspace_floats, int rows, void *stream);
+
+/* SelfAttention.forward in training mode (transformer.py:58-76) on the fused qkv (B*T, 3*n_heads*head_dim) bf16 = [q | k | v]:
+ *     out (B*T, n_heads*head_dim) bf16 = dropout(softmax(scale q k^T)) v,   lse (B, n_heads, T) fp32 (log2 units)
+ * dropout element index e = ((b * n_heads + h) * T + i) * T + j.  head_dim in {64, 96}; T up to 487 (shared-memory bound). */
+int sfb_attention_train_fwd(const void *qkv, void *out, float *lse, int B, int T, int n_heads, int head_dim, float scale, float p_drop,
+                            uint64_t seed, uint32_t site, void *stream);
+/* backward of the above: dqkv (B*T, 3*n_heads*head_dim) bf16 from d_out; P is recomputed from qkv and lse, the mask from the counter.
+ * delta (B, n_heads, T) fp32 is scratch (dO . O per row). */
+int sfb_attention_train_bwd(const void *qkv, const void *out, const void *d_out, const float *lse, float *delta, void *dqkv, int B, int T,
+                            int n_heads, int head_dim, float scale, float p_drop, uint64_t seed, uint32_t site, void *stream);
+
+/* backward of sfb_sync_head (sync_model.py:169-172): dx (B, T, 768) fp32 is zeroed and its token-0 rows receive the gradient;
+ * dln_w / dln_b (768), dW (n_cls, 768), dbias (n_cls) fp32; scratch: B * 3 * 768 floats. */
+int sfb_sync_head_bwd(const float *x, int T, const float *ln_w, const float *ln_b, float eps, const float *W, const float *dlogits, int B,
+                      int n_cls, float *dx, float *dln_w, float *dln_b, float *dW, float *dbias, float *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -322,3 +322,84 @@ def avclip_features(sd, vis: Tensor, aud: Tensor, dtype=torch.float32):
     vf = extract_vfeats(sd, vis, dtype).mean(2).reshape(-1, D)
     af = extract_afeats(sd, aud, dtype).mean(2).reshape(-1, D)
     return F.normalize(vf, dim=-1), F.normalize(af, dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# N3: training-mode forward of the synchronisation module with EXPLICIT dropout multipliers, so that torch
+# autograd on this restatement gives the reference gradients for a known mask (scripts/train_utils.py:373-386 drives
+# loss.backward() through model/sync_model.py:55-62, 150-173 and modules/transformer.py:58-97).
+# Pinned by tests/golden/sync_train_b2s2.npz (the reference's own modules in train mode with the same multipliers injected in
+# place of its nn.Dropout instances; tests/golden/make_golden_train.py).
+# ----------------------------------------------------------------------------------------------------------
+def train_sites(n_layer: int = S_DEPTH) -> dict:
+    """Dropout layer -> site id of the counter-based mask (csrc/philox.cuh)."""
+    sites = {'embd': 0}
+    for i in range(n_layer):
+        sites[f'attn{i}'], sites[f'resid_attn{i}'], sites[f'resid_mlp{i}'] = 1 + 3 * i, 2 + 3 * i, 3 + 3 * i
+    return sites
+
+
+def train_multipliers(B: int, T: int, seed: int, embd_pdrop: float = 0.1, resid_pdrop: float = 0.1, attn_pdrop: float = 0.1) -> Dict[str, Tensor]:
+    """The multipliers (0 or 1 / (1 - p)) the CUDA kernels apply for `seed`: embd / resid_* (B, T, 768), attn* (B, 8, T, T)."""
+    from . import philox
+    out = {}
+    for name, site in train_sites().items():
+        if name == 'embd':
+            shape, p = (B, T, D), embd_pdrop
+        elif name.startswith('attn'):
+            shape, p = (B, S_HEADS, T, T), attn_pdrop
+        else:
+            shape, p = (B, T, D), resid_pdrop
+        out[name] = torch.from_numpy(philox.dropout_multiplier(shape, p, seed, site))
+    return out
+
+
+def sync_block_train(sd, i: int, x: Tensor, mult: Optional[Dict[str, Tensor]]) -> Tensor:
+    """Block.forward transformer.py:94-97 in training mode: attn_drop on the softmax output (:74), resid_drop after proj (:76)
+    and after the MLP (:92).  mult=None -> dropout off."""
+    p = f'transformer.blocks.{i}.'
+    B, T, _ = x.shape
+    h, d = S_HEADS, D // S_HEADS
+    m = (lambda k: 1.0) if mult is None else (lambda k: mult[k].to(x.dtype))
+    y = _ln(x, sd[p + 'ln1.weight'], sd[p + 'ln1.bias'], EPS_S)
+    sp = lambda t: t.reshape(B, T, h, d).permute(0, 2, 1, 3)
+    q = sp(_lin(y, sd[p + 'attn.query.weight'], sd[p + 'attn.query.bias']))
+    k = sp(_lin(y, sd[p + 'attn.key.weight'], sd[p + 'attn.key.bias']))
+    v = sp(_lin(y, sd[p + 'attn.value.weight'], sd[p + 'attn.value.bias']))
+    att = torch.softmax((q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(d)), dim=-1) * m(f'attn{i}')
+    a = (att @ v).permute(0, 2, 1, 3).reshape(B, T, D)
+    x = x + _lin(a, sd[p + 'attn.proj.weight'], sd[p + 'attn.proj.bias']) * m(f'resid_attn{i}')
+    y = _ln(x, sd[p + 'ln2.weight'], sd[p + 'ln2.bias'], EPS_S)
+    y = _gelu(_lin(y, sd[p + 'mlp.0.weight'], sd[p + 'mlp.0.bias']))
+    return x + _lin(y, sd[p + 'mlp.2.weight'], sd[p + 'mlp.2.bias']) * m(f'resid_mlp{i}')
+
+
+def sync_head_train(sd, vfeat: Tensor, afeat: Tensor, mult: Optional[Dict[str, Tensor]] = None, head: str = 'off_head') -> Tensor:
+    """sync_head() in training mode; `sd` tensors may require grad (no dtype cast is applied: pass fp32 / fp64 leaves)."""
+    B, S = vfeat.shape[:2]
+    v = _lin(vfeat, sd['vproj.weight'], sd['vproj.bias']).reshape(B, S * 8, D)
+    a = _lin(afeat, sd['aproj.weight'], sd['aproj.bias']).reshape(B, S * 6, D)
+    t = 'transformer.'
+    v = _ln(v, sd[t + 'vis_in_lnorm.weight'], sd[t + 'vis_in_lnorm.bias'], EPS_S)
+    a = _ln(a, sd[t + 'aud_in_lnorm.weight'], sd[t + 'aud_in_lnorm.bias'], EPS_S)
+    x = torch.cat([sd[t + 'OFF_tok'].expand(B, 1, D), v, sd[t + 'MOD_tok'].expand(B, 1, D), a], dim=1)
+    x = x + sd[t + 'pos_emb_cfg.pos_emb']
+    if mult is not None:
+        x = x * mult['embd'].to(x.dtype)                       # self.drop sync_model.py:168
+    for i in range(S_DEPTH):
+        x = sync_block_train(sd, i, x, mult)
+    x = _ln(x, sd[t + 'ln_f.weight'], sd[t + 'ln_f.bias'], EPS_S)
+    return _lin(x[:, 0], sd[t + head + '.weight'], sd[t + head + '.bias'])
+
+
+def sync_train_grads(sd, vfeat: Tensor, afeat: Tensor, targets: Tensor, mult: Optional[Dict[str, Tensor]] = None, head: str = 'off_head',
+                     dtype=torch.float32, loss_scale: float = 1.0):
+    """loss = cross_entropy(logits, targets) (compute_loss sync_model.py:91-99); returns (loss, logits, {name: d loss / d param}) for
+    every parameter of vproj / aproj / transformer (the trainable set of configs/sync.yaml with frozen extractors)."""
+    names = [k for k in sd if k.split('.')[0] in ('vproj', 'aproj', 'transformer')]
+    leaves = {k: sd[k].detach().to(dtype).clone().requires_grad_(True) for k in names}
+    with torch.enable_grad():
+        logits = sync_head_train(leaves, vfeat.to(dtype), afeat.to(dtype), mult, head)
+        loss = F.cross_entropy(logits, targets)
+        grads = torch.autograd.grad(loss * loss_scale, [leaves[k] for k in names])
+    return loss.detach(), logits.detach(), {k: g for k, g in zip(names, grads)}

@@ -4,7 +4,7 @@ There is no CPU or eager-PyTorch fallback: if the library is missing or fails to
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libsynchformer_b200.so')
@@ -53,6 +53,21 @@ SIGNATURES = {
     'sfb_cast_f32_bf16': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     'sfb_mel_frontend': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'sfb_mel_frontend_clip': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    # N3: training step of the synchronisation module
+    'sfb_dropout': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_uint64, c_uint32, c_void_p]),
+    'sfb_gelu_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    'sfb_gelu_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'sfb_transpose_bf16': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    'sfb_colsum': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    'sfb_layernorm_bwd_workspace_floats': (c_int, [c_int]),
+    'sfb_layernorm_bwd': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_float, c_void_p, c_int64, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'sfb_attention_train_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, c_uint32,
+                                        c_void_p]),
+    'sfb_attention_train_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                        c_float, c_uint64, c_uint32, c_void_p]),
+    'sfb_sync_head_bwd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

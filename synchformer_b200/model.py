@@ -10,7 +10,8 @@ Parameters are ordinary fp32 `nn.Parameter`s under the reference's names (so `lo
 keeps three matrices) are cached per device and refreshed when a parameter's version counter changes.
 
 All arithmetic runs in the CUDA kernels of `libsynchformer_b200.so` (see ops.py); PyTorch only owns memory and
-streams.  Inference only (eval / no_grad): the backward of the sync module is a "next" row.
+streams.  The feature extractors are inference-only (frozen, as configs/sync.yaml trains them); the synchronisation module
+(vproj / aproj / transformer) also trains: in train mode its forward applies dropout and is differentiable (train.py).
 """
 import logging
 import math
@@ -19,7 +20,7 @@ from typing import Any, Dict, Mapping, Optional
 import torch
 from torch import nn
 
-from . import ops
+from . import ops, train
 from .schema import D, state_dict_schema
 
 EPS_V, EPS_A, EPS_S = 1e-6, 1e-12, 1e-5
@@ -326,6 +327,17 @@ class AST(_KernelModule):
         return feats.mean(dim=2) if self.time_pool else feats
 
 
+class _NoDropout:
+    """View of a GlobalTransformer with every dropout probability forced to 0 (gradients in eval mode)."""
+    tok_pdrop = embd_pdrop = resid_pdrop = attn_pdrop = 0.0
+
+    def __init__(self, tr):
+        self._tr = tr
+
+    def __getattr__(self, name):
+        return getattr(self._tr, name)
+
+
 class GlobalTransformer(_KernelModule):
     """Synchronisation transformer (sync_model.py:117-173): 3 pre-norm blocks, 8 heads x 96, LN eps 1e-5, erf GELU.
     `pos_emb_cfg.pos_emb` is the RandInitPositionalEncoding table (modules/transformer.py:120-130)."""
@@ -368,9 +380,13 @@ class GlobalTransformer(_KernelModule):
     def forward(self, v: torch.Tensor, a: torch.Tensor, targets=None, attempt_to_apply_heads=True):
         """v (B, 8S, 768), a (B, 6S, 768) projected features -> logits (B, n_cls).  sync_model.py:150-173 (eval: dropouts are identity)."""
         ops.require_cuda(v, 'v')
-        if self.training and max(self.tok_pdrop, self.embd_pdrop, self.resid_pdrop, self.attn_pdrop) > 0 and torch.is_grad_enabled():
-            raise NotImplementedError('training-mode dropout / backward of the sync module is not implemented yet (SURVEY.md §8f N3); '
-                                      'call under model.eval() / torch.no_grad()')
+        if self.training or (torch.is_grad_enabled() and (v.requires_grad or a.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            # SURVEY.md §8f N3: dropout + autograd-visible forward / hand-written backward (train.py); eval + no_grad takes the path below
+            if not attempt_to_apply_heads and self._HEAD == 'off_head':
+                raise NotImplementedError('training without the classification head is not implemented')
+            if not self.training:                                                   # eval-mode gradients: same kernels, dropout off
+                return train.sync_transformer(_NoDropout(self), v, a)
+            return train.sync_transformer(self, v, a)
         B, Sv, _ = v.shape
         Sa = a.shape[1]
         if Sv % 8 or Sa % 6 or Sv // 8 != Sa // 6:
@@ -464,6 +480,11 @@ class Synchformer(nn.Module):
         """vproj / aproj (sync_model.py:55-56) + segment flattening (:59-62).  (B,S,8,768),(B,S,6,768) -> (B,8S,768),(B,6S,768) fp32."""
         B, S = vis.shape[:2]
         Wp = self._proj_weights()
+        if self.training or (torch.is_grad_enabled() and (vis.requires_grad or aud.requires_grad or self.vproj.weight.requires_grad
+                                                          or self.aproj.weight.requires_grad)):
+            v = train.linear(vis.float().contiguous().view(-1, D), self.vproj.weight, self.vproj.bias, Wp['v'])        # N3: differentiable
+            a = train.linear(aud.float().contiguous().view(-1, D), self.aproj.weight, self.aproj.bias, Wp['a'])
+            return v.view(B, S * 8, D), a.view(B, S * 6, D)
         v = ops.gemm(ops.cast_bf16(vis.float().contiguous().view(-1, D)), Wp['v'], self.vproj.bias.detach(), out_f32=True)
         a = ops.gemm(ops.cast_bf16(aud.float().contiguous().view(-1, D)), Wp['a'], self.aproj.bias.detach(), out_f32=True)
         return v.view(B, S * 8, D), a.view(B, S * 6, D)
@@ -472,6 +493,12 @@ class Synchformer(nn.Module):
     def forward(self, vis: torch.Tensor, aud: torch.Tensor, targets: torch.Tensor = None, for_loop=False, vis_mask: torch.Tensor = None,
                 aud_mask: torch.Tensor = None, loss_fn=None):
         """vis (B, S, Tv=16, C=3, H=224, W=224), aud (B, S, 1, F=128, Ta=66) -> (loss | None, logits (B, n_cls))."""
+        if self.training and torch.is_grad_enabled() and any(
+                p.requires_grad for m in (self.vfeat_extractor, self.afeat_extractor) for n, p in m.named_parameters()
+                if not n.startswith('patch_embed.')):
+            raise NotImplementedError('the backward of the feature extractors is not implemented (SURVEY.md §8f N1): freeze them as '
+                                      'configs/sync.yaml:8,20 (is_trainable: False) + scripts/train_utils.py:199-204 do, i.e. '
+                                      'requires_grad_(False) and .eval() on vfeat_extractor / afeat_extractor')
         vis = self.extract_vfeats(vis, for_loop, vis_mask=vis_mask)
         aud = self.extract_afeats(aud, for_loop, aud_mask=aud_mask)
         v, a = self.project(vis, aud)

@@ -250,3 +250,143 @@ def mel_frontend_clip(wave: torch.Tensor, n_segments: int, a_start: int, a_strid
           'sfb_mel_frontend_clip')
     _count()
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N3: training kernels of the synchronisation module (see include/synchformer_b200.h, "N3")
+# ------------------------------------------------------------------------------------------------------------------
+def dropout(x: torch.Tensor, p: float, seed: int, site: int, *, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            out_bf16: bool = False) -> torch.Tensor:
+    """out = residual + x * mask / (1 - p) with the counter-based mask keep(seed, site, linear index); x / residual fp32."""
+    require_cuda(x, 'x')
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() % 4 == 0
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == x.shape
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    assert out.is_contiguous() and out.shape == x.shape and out.dtype == (torch.bfloat16 if out_bf16 else torch.float32)
+    check(_lib.load().sfb_dropout(_p(x), _p(residual), _p(out), int(out_bf16), x.numel(), float(p), int(seed), int(site), _stream(x)), 'sfb_dropout')
+    _count()
+    return out
+
+
+def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, 'x')
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0
+    y = torch.empty_like(x)
+    check(_lib.load().sfb_gelu_fwd(_p(x), _p(y), x.numel(), _stream(x)), 'sfb_gelu_fwd')
+    _count()
+    return y
+
+
+def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, 'x')
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous() and x.shape == dy.shape
+    assert x.numel() % 8 == 0
+    dx = torch.empty_like(x)
+    check(_lib.load().sfb_gelu_bwd(_p(dy), _p(x), _p(dx), x.numel(), _stream(x)), 'sfb_gelu_bwd')
+    _count()
+    return dx
+
+
+def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
+    """(R, C) bf16 (row stride may exceed C) -> (C, R) bf16 view of a (C, ceil8(R)) buffer whose padding columns are zero."""
+    require_cuda(x, 'x')
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    ld = (R + 7) // 8 * 8
+    out = torch.empty((C, ld), device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().sfb_transpose_bf16(_p(x), x.stride(0), R, C, _p(out), ld, _stream(x)), 'sfb_transpose_bf16')
+    _count()
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """(M, N) bf16 / fp32 -> (N,) fp32 column sums (deterministic)."""
+    require_cuda(x, 'x')
+    assert x.dtype in (torch.bfloat16, torch.float32) and x.dim() == 2 and x.stride(1) == 1
+    M, N = x.shape
+    out = torch.empty((N,), device=x.device, dtype=torch.float32)
+    parts = min(64, (M + 63) // 64)
+    ws = torch.empty((parts * N,), device=x.device, dtype=torch.float32) if parts > 1 else None
+    check(_lib.load().sfb_colsum(_p(x), int(x.dtype == torch.bfloat16), x.stride(0), M, N, _p(out), _p(ws), 0 if ws is None else ws.numel(),
+                                 _stream(x)), 'sfb_colsum')
+    _count(2 if parts > 1 else 1)
+    return out
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float, *, dx: Optional[torch.Tensor] = None,
+                  accumulate: bool = False, rows: Optional[int] = None, group: Optional[int] = None, group_stride: Optional[int] = None,
+                  offset: int = 0):
+    """LayerNorm backward over 768 (fp32).  x (rows, 768); dy row of output row r = (r // group) * group_stride + offset + r % group.
+    Returns (dx (rows, 768), dgamma (768,), dbeta (768,)); accumulate=True adds into the given dx."""
+    require_cuda(x, 'x')
+    assert dy.dtype == torch.float32 and x.dtype == torch.float32 and dy.dim() == 2 and x.dim() == 2 and dy.stride(1) == 1 and x.stride(1) == 1
+    assert x.shape[1] == D and dy.shape[1] == D
+    if rows is None:
+        rows = x.shape[0]
+    if group is None:
+        group, group_stride = rows, rows
+    assert ((rows - 1) // group) * group_stride + offset + (rows - 1) % group < dy.shape[0], 'dy row gather out of range'
+    assert x.shape[0] >= rows
+    if dx is None:
+        assert not accumulate
+        dx = torch.empty((rows, D), device=x.device, dtype=torch.float32)
+    assert dx.dtype == torch.float32 and dx.shape[0] >= rows and dx.shape[1] == D and dx.stride(1) == 1
+    lib = _lib.load()
+    dgb = torch.empty((2, D), device=x.device, dtype=torch.float32)
+    n_ws = lib.sfb_layernorm_bwd_workspace_floats(rows)
+    ws = torch.empty((n_ws,), device=x.device, dtype=torch.float32)
+    check(lib.sfb_layernorm_bwd(_p(dy), dy.stride(0), group, group_stride, offset, _p(x), x.stride(0), _p(gamma), eps, _p(dx), dx.stride(0),
+                                int(accumulate), _p(dgb[0]), _p(dgb[1]), _p(ws), n_ws, rows, _stream(x)), 'sfb_layernorm_bwd')
+    _count(2)
+    return dx, dgb[0], dgb[1]
+
+
+def attention_train_fwd(qkv: torch.Tensor, B: int, T: int, n_heads: int, head_dim: int, scale: float, p: float, seed: int, site: int):
+    """qkv (B*T, 3*n_heads*head_dim) bf16 -> (out (B*T, n_heads*head_dim) bf16, lse (B, n_heads, T) fp32)."""
+    require_cuda(qkv, 'qkv')
+    Dm = n_heads * head_dim
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * T, 3 * Dm)
+    out = torch.empty((B * T, Dm), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, n_heads, T), device=qkv.device, dtype=torch.float32)
+    check(_lib.load().sfb_attention_train_fwd(_p(qkv), _p(out), _p(lse), B, T, n_heads, head_dim, scale, float(p), int(seed), int(site),
+                                              _stream(qkv)), 'sfb_attention_train_fwd')
+    _count()
+    return out, lse
+
+
+def attention_train_bwd(qkv: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, lse: torch.Tensor, B: int, T: int, n_heads: int,
+                        head_dim: int, scale: float, p: float, seed: int, site: int) -> torch.Tensor:
+    """-> dqkv (B*T, 3*n_heads*head_dim) bf16."""
+    require_cuda(qkv, 'qkv')
+    Dm = n_heads * head_dim
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * T, 3 * Dm)
+    for t in (out, d_out):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == (B * T, Dm)
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * n_heads * T
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    check(_lib.load().sfb_attention_train_bwd(_p(qkv), _p(out), _p(d_out), _p(lse), _p(delta), _p(dqkv), B, T, n_heads, head_dim, scale, float(p),
+                                              int(seed), int(site), _stream(qkv)), 'sfb_attention_train_bwd')
+    _count(2)
+    return dqkv
+
+
+def sync_head_bwd(x: torch.Tensor, T: int, ln_w: torch.Tensor, ln_b: torch.Tensor, eps: float, W: torch.Tensor, dlogits: torch.Tensor, B: int):
+    """backward of sync_head: -> (dx (B*T, 768) fp32 [zero except token 0 of each clip], dln_w, dln_b, dW (n_cls, 768), dbias (n_cls))."""
+    require_cuda(x, 'x')
+    n_cls = W.shape[0]
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape == (B * T, D)
+    assert dlogits.dtype == torch.float32 and dlogits.is_contiguous() and dlogits.shape == (B, n_cls)
+    assert W.dtype == torch.float32 and W.is_contiguous()
+    dev = x.device
+    dx = torch.empty((B * T, D), device=dev, dtype=torch.float32)
+    dln = torch.empty((2, D), device=dev, dtype=torch.float32)
+    dW = torch.empty((n_cls, D), device=dev, dtype=torch.float32)
+    db = torch.empty((n_cls,), device=dev, dtype=torch.float32)
+    scratch = torch.empty((B * 3 * D,), device=dev, dtype=torch.float32)
+    check(_lib.load().sfb_sync_head_bwd(_p(x), T, _p(ln_w), _p(ln_b), eps, _p(W), _p(dlogits), B, n_cls, _p(dx), _p(dln[0]), _p(dln[1]), _p(dW),
+                                        _p(db), _p(scratch), _stream(x)), 'sfb_sync_head_bwd')
+    _count(2)
+    return dx, dln[0], dln[1], dW, db

@@ -21,6 +21,13 @@ def golden_dir():
 @pytest.fixture(scope='session')
 def cuda_device():
     import torch
+    if os.environ.get('SFB_TEST_DRY_RUN') == '1' and not torch.cuda.is_available():
+        # developer aid, never set by the driver: run the *test logic* of tests/test_train_gpu.py on the CPU stand-ins of
+        # tests/fake_ops.py (shapes, tolerances, oracle plumbing), so that on the GPU box only the kernels themselves can fail
+        import fake_ops
+        mp = pytest.MonkeyPatch()
+        fake_ops.install(mp, round_bf16=True)
+        return torch.device('cpu')
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     from synchformer_b200 import ops
