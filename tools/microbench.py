@@ -48,6 +48,11 @@ def main():
         ms = timeit(lambda: ops.gemm(a, W, bias, **kw))
         fl = 2.0 * M * N * K
         res['gemm ' + name] = {'ms': ms, 'TFLOPs': fl / ms / 1e9}
+        if os.environ.get('SFB_MB_CUBLAS') == '1':
+            # library yardstick for the same shape: plain cuBLAS bf16 GEMM through torch (bias only, no GELU / residual / fp32 output), so
+            # it is a LOWER bound on what a library path would need for the fused op.  Measurement aid only, never on the product path.
+            cub = timeit(lambda: torch.nn.functional.linear(a, W, bias.bfloat16()))
+            res['gemm ' + name].update({'cublas_ms': cub, 'cublas_TFLOPs': fl / cub / 1e9})
     ms = timeit(lambda: ops.layernorm(x, g, b, 1e-6, out=ln))
     res['layernorm'] = {'ms': ms, 'GBs': M * D * 6 / ms / 1e6}
     row, seg = 3 * D, 1569 * 3 * D
