@@ -53,3 +53,47 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     sass = subprocess.run([cuobjdump, '-sass', build.LIB], capture_output=True, text=True).stdout
     for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG', 'HMMA'):
         assert mnemonic in sass, mnemonic
+
+
+def test_training_entry_points_validate_then_reach_the_launch():
+    """N3 entry points, called the way ops.py calls them but with fake (never dereferenced) device addresses on a box WITHOUT a GPU:
+    a well-formed call gets through the host-side validation and fails only at the CUDA launch (SFB_E_CUDA = -2), a malformed one is
+    rejected before (SFB_E_INVALID = -1 / SFB_E_UNSUPPORTED = -3).  Catches argument-order / ctypes-signature slips without hardware."""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('would launch kernels on fake addresses')
+    lib = _lib.load()
+    P = lambda k: ctypes.c_void_p(0x10000 * (k + 1))          # 64 KB-aligned fake addresses
+    B, T, M = 2, 30, 60
+    ok = [
+        lib.sfb_dropout(P(0), P(1), P(2), 0, M * 768, 0.1, 12345678901234, 3, None),
+        lib.sfb_dropout(P(0), None, P(2), 1, M * 768, 0.0, 0, 0, None),
+        lib.sfb_gelu_fwd(P(0), P(1), M * 3072, None),
+        lib.sfb_gelu_bwd(P(0), P(1), P(2), M * 3072, None),
+        lib.sfb_transpose_bf16(P(0), 768, M, 768, P(1), 64, None),
+        lib.sfb_colsum(P(0), 1, 768, M, 768, P(1), None, 0, None),
+        lib.sfb_colsum(P(0), 0, 2304, 5000, 2304, P(1), P(2), 64 * 2304, None),
+        lib.sfb_layernorm_bwd(P(0), 768, 16, 30, 1, P(1), 768, P(2), 1e-5, P(3), 768, 0, ctypes.c_void_p(0x90000), ctypes.c_void_p(0x90000 + 768 * 4),
+                              P(5), lib.sfb_layernorm_bwd_workspace_floats(32), 32, None),
+        lib.sfb_attention_train_fwd(P(0), P(1), P(2), B, T, 8, 96, 0.102, 0.1, 99, 1, None),
+        lib.sfb_attention_train_bwd(P(0), P(1), P(2), P(3), P(4), P(5), B, T, 8, 96, 0.102, 0.1, 99, 1, None),
+        lib.sfb_sync_head_bwd(P(0), T, P(1), P(2), 1e-5, P(3), P(4), B, 21, P(5), P(6), P(7), P(8), P(9), P(10), None),
+    ]
+    assert ok == [-2] * len(ok), (ok, lib.sfb_last_error())
+    assert lib.sfb_layernorm_bwd_workspace_floats(32) == 4 * 2 * 768 and lib.sfb_layernorm_bwd_workspace_floats(10 ** 6) <= 2 * 148 * 2 * 768
+    bad = [
+        lib.sfb_dropout(P(0), None, P(2), 0, 6, 0.1, 0, 0, None),                                   # n % 4
+        lib.sfb_dropout(P(0), None, P(2), 0, 8, 1.0, 0, 0, None),                                   # p outside [0, 1)
+        lib.sfb_gelu_fwd(P(0), P(1), 12, None),                                                     # n % 8
+        lib.sfb_transpose_bf16(P(0), 768, M, 768, P(1), 56, None),                                  # ld_out < R
+        lib.sfb_colsum(P(0), 1, 768, M, 767, P(1), None, 0, None),                                  # odd N
+        lib.sfb_layernorm_bwd(P(0), 768, 16, 30, 1, P(1), 768, P(2), 1e-5, P(3), 768, 0, P(4), P(6), P(5), 10 ** 6, 32, None),   # dbeta != dgamma + 768
+        lib.sfb_layernorm_bwd(P(0), 768, 16, 30, 1, P(1), 768, P(2), 1e-5, P(3), 768, 0, ctypes.c_void_p(0x90000), ctypes.c_void_p(0x90000 + 3072),
+                              P(5), 100, 32, None),                                                 # workspace too small
+        lib.sfb_attention_train_fwd(P(0), P(1), P(2), B, T, 8, 80, 0.1, 0.1, 99, 1, None),          # head_dim
+        lib.sfb_sync_head_bwd(P(0), T, P(1), P(2), 1e-5, P(3), P(4), B, 65, P(5), P(6), P(7), P(8), P(9), P(10), None),          # n_cls > 64
+    ]
+    assert bad == [-1] * len(bad), bad
+    assert lib.sfb_attention_train_fwd(P(0), P(1), P(2), 1, 600, 8, 96, 0.1, 0.0, 0, 0, None) == -3   # T too long for shared memory
+    assert b'shared memory' in lib.sfb_last_error()
