@@ -1,0 +1,43 @@
+"""Bind `synchformer_b200.ops` to the CPU SIMT emulator build of the N3 kernels (tests/emu/_build/libsfb_emu.so).
+
+TEST INFRASTRUCTURE ONLY.  `install(monkeypatch)` makes the REAL wrappers of ops.py (dropout, gelu_fwd / gelu_bwd, transpose_bf16,
+colsum, layernorm_bwd, attention_train_fwd / _bwd, sync_head_bwd) call the REAL C-ABI entry points and the REAL kernel code, compiled
+for the emulator, on CPU tensors; the kernels that were verified on hardware in round 1 and are not part of N3 (gemm, layernorm,
+sync_tokens, sync_head, cast) are served by the torch stand-ins of tests/fake_ops.py with real bf16 dtypes.
+"""
+import ctypes
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+EMULATED = ('sfb_dropout', 'sfb_gelu_fwd', 'sfb_gelu_bwd', 'sfb_transpose_bf16', 'sfb_colsum', 'sfb_layernorm_bwd_workspace_floats',
+            'sfb_layernorm_bwd', 'sfb_attention_train_fwd', 'sfb_attention_train_bwd', 'sfb_sync_head_bwd', 'sfb_last_error')
+STAND_INS = ('require_cuda', 'cast_bf16', 'gemm', 'layernorm', 'sync_tokens', 'sync_head')
+
+_emu = None
+
+
+def load():
+    global _emu
+    if _emu is None:
+        from synchformer_b200 import _lib
+        from emu import build_emu
+        lib = ctypes.CDLL(build_emu.build())
+        for name in EMULATED:
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = _lib.SIGNATURES[name]
+        lib.emu_launch_count.restype = ctypes.c_long
+        _emu = lib
+    return _emu
+
+
+def install(monkeypatch):
+    import fake_ops
+    from synchformer_b200 import _lib, ops
+    lib = load()
+    monkeypatch.setattr(_lib, '_lib', lib)                      # _lib.load() returns the cached handle
+    monkeypatch.setattr(ops, '_stream', lambda t: None)
+    fake_ops.install(monkeypatch, round_bf16=True, names=STAND_INS, real_dtypes=True)
+    return lib

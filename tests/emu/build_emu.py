@@ -1,0 +1,112 @@
+"""Build `tests/emu/_build/libsfb_emu.so`: the N3 kernel sources compiled for the CPU SIMT emulator (tests/emu/common.cuh).
+
+TEST INFRASTRUCTURE ONLY.  The sources are taken from synchformer_b200/csrc/ as they are; the only textual rewrites are the two that g++
+cannot express through macros:
+  * `kernel<<<grid, block, smem, stream>>>(args);`  ->  `emu::launch(dim3(grid), dim3(block), smem, [&]() { kernel(args); });`
+  * `extern __shared__ ... smem_raw[];`             ->  `unsigned char *smem_raw = emu::dyn_smem();`
+`#include "common.cuh"` resolves to the shim next to the generated copy; `philox.cuh` is the real one (via -I csrc).
+"""
+import hashlib
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(REPO, 'synchformer_b200', 'csrc')
+OUT = os.path.join(HERE, '_build')
+LIB = os.path.join(OUT, 'libsfb_emu.so')
+SOURCES = ['train.cu', 'attention_train.cu']
+CUDA_INC = os.environ.get('CUDA_INC', '/usr/local/cuda/include')
+
+
+def _match(text: str, start: int, open_ch: str, close_ch: str) -> int:
+    """index just past the bracket that closes the one at text[start]"""
+    depth = 0
+    for i in range(start, len(text)):
+        if text[i] == open_ch:
+            depth += 1
+        elif text[i] == close_ch:
+            depth -= 1
+            if depth == 0:
+                return i + 1
+    raise ValueError('unbalanced')
+
+
+def _split_top(s: str):
+    parts, depth, cur = [], 0, ''
+    for ch in s:
+        if ch in '([{<':
+            depth += 1
+        elif ch in ')]}>':
+            depth -= 1
+        if ch == ',' and depth == 0:
+            parts.append(cur.strip())
+            cur = ''
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
+def rewrite_launches(text: str) -> str:
+    out, pos = '', 0
+    while True:
+        k = text.find('<<<', pos)
+        if k < 0:
+            return out + text[pos:]
+        name_start = k
+        while name_start > 0 and re.match(r'[A-Za-z0-9_:<>]', text[name_start - 1]):
+            name_start -= 1
+        cfg_end = text.index('>>>', k)
+        cfg = _split_top(text[k + 3:cfg_end])
+        assert 2 <= len(cfg) <= 4, cfg
+        args_start = cfg_end + 3
+        assert text[args_start] == '(', text[args_start:args_start + 20]
+        args_end = _match(text, args_start, '(', ')')
+        kernel, args = text[name_start:k], text[args_start:args_end]
+        smem = cfg[2] if len(cfg) > 2 else '0'
+        out += text[pos:name_start] + f'emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), {smem}, [&]() {{ {kernel}{args}; }})'
+        pos = args_end
+    return out
+
+
+def transform(text: str) -> str:
+    text = re.sub(r'extern\s+__shared__\s+__align__\(\d+\)\s+unsigned char (\w+)\[\];', r'unsigned char *\1 = emu::dyn_smem();', text)
+    return rewrite_launches(text)
+
+
+def build(force: bool = False) -> str:
+    os.makedirs(OUT, exist_ok=True)
+    h = hashlib.sha256()
+    for f in SOURCES + ['philox.cuh']:
+        h.update(open(os.path.join(CSRC, f), 'rb').read())
+    for f in ('common.cuh', 'build_emu.py'):
+        h.update(open(os.path.join(HERE, f), 'rb').read())
+    stamp = os.path.join(OUT, 'stamp')
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
+        return LIB
+    gen = []
+    for f in SOURCES:
+        dst = os.path.join(OUT, f.replace('.cu', '_emu.cpp'))
+        with open(dst, 'w') as fh:
+            fh.write(transform(open(os.path.join(CSRC, f)).read()))
+        gen.append(dst)
+    with open(os.path.join(OUT, 'common.cuh'), 'w') as fh:          # quote-includes look next to the including file first
+        fh.write('#include "../common.cuh"\n')
+    extra = os.path.join(OUT, 'emu_exports.cpp')
+    with open(extra, 'w') as fh:
+        fh.write('#define EMU_MAIN_TU 1\n#include "common.cuh"\nextern "C" const char *sfb_last_error(void) { return sfb::err_buf(); }\n'
+                 'extern "C" long emu_launch_count(void) { return emu::S().launches; }\n')
+    cmd = ['g++', '-O2', '-g', '-std=c++17', '-shared', '-fPIC', '-w', '-I', OUT, '-I', CSRC, '-I', CUDA_INC, '-o', LIB] + gen + [extra]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('emulator build failed:\n' + r.stdout + r.stderr)
+    with open(stamp, 'w') as fh:
+        fh.write(h.hexdigest())
+    return LIB
+
+
+if __name__ == '__main__':
+    import sys
+    print(build(force='--force' in sys.argv))

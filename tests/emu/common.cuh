@@ -1,0 +1,324 @@
+// CPU SIMT emulator shim — TEST INFRASTRUCTURE ONLY (tests/emu/build_emu.py compiles the UNMODIFIED kernel sources
+// synchformer_b200/csrc/train.cu and attention_train.cu against this header instead of the real common.cuh).
+//
+// Purpose: execute the exact device code of the N3 kernels (and the exact host launch code of their C-ABI entry points) on a box
+// without a GPU, so that indexing, barrier placement, shared-memory layout and launch configuration are checked before the first
+// hardware run.  It is not a performance model and knows nothing about sm_100a; it only gives CUDA's SIMT semantics to g++:
+//   * every CUDA thread of a block is a ucontext coroutine; blocks run one after another
+//   * __syncthreads / __syncwarp / __shfl_xor_sync are rendezvous points of the coroutine scheduler (exited threads do not block)
+//   * __shared__ variables are function-level statics (one instance, blocks are sequential); dynamic shared memory is one buffer
+//   * kernel<<<grid, block, smem, stream>>>(args) is rewritten by build_emu.py into emu::launch(grid, block, smem, [&]{ kernel(args); })
+// A deadlock (a barrier that not every live thread reaches) aborts with a message instead of hanging.
+#pragma once
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <algorithm>
+#include <functional>
+#include <vector>
+
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define __shared__ static
+#define __CUDA_NO_BFLOAT16_OPERATORS__
+
+#include <vector_types.h>
+#include <vector_functions.h>
+#include <cuda_bf16.h>
+
+#include "../../include/synchformer_b200.h"
+
+// the CUDA headers above declare the runtime API (types are reused); the four calls the entry points make are redirected here
+inline const char *emu_cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t emu_cudaGetLastError() { return cudaSuccess; }
+template <typename K>
+inline cudaError_t emu_cudaFuncSetAttribute(K, int, int bytes) { return bytes <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidValue; }
+inline cudaError_t emu_cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) {
+    memset(p, v, n);
+    return cudaSuccess;
+}
+#define cudaGetErrorString emu_cudaGetErrorString
+#define cudaGetLastError emu_cudaGetLastError
+#define cudaFuncSetAttribute emu_cudaFuncSetAttribute
+#define cudaMemsetAsync emu_cudaMemsetAsync
+
+namespace emu {
+
+// Context switch.  glibc's swapcontext makes a sigprocmask system call per switch (~1 us; a 600 x 3072 transpose is 470 k threads), so
+// on x86-64 the coroutines switch with a 14-instruction callee-saved-register swap instead; elsewhere ucontext is the fallback.
+#if defined(__x86_64__)
+#define EMU_FAST_SWITCH 1
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+#ifdef EMU_MAIN_TU                      // defined once, in the translation unit build_emu.py generates for the exports
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+#endif
+#else
+#define EMU_FAST_SWITCH 0
+#endif
+
+struct Thread {
+#if EMU_FAST_SWITCH
+    void *sp = nullptr;
+#else
+    ucontext_t ctx;
+#endif
+    char *stack = nullptr;
+    int state = 0;   // 0 runnable, 1 at __syncthreads, 2 at a warp rendezvous, 3 exited
+};
+
+inline uint3 &tid() { static uint3 v; return v; }
+inline uint3 &bid() { static uint3 v; return v; }
+inline dim3 &bdim() { static dim3 v; return v; }
+inline dim3 &gdim() { static dim3 v; return v; }
+inline unsigned char *&dyn_smem() { static unsigned char *p = nullptr; return p; }
+
+struct Sched {
+    std::vector<Thread> threads;
+    std::vector<uint64_t> slot;       // per-thread exchange slot for shuffles
+#if EMU_FAST_SWITCH
+    void *main_sp = nullptr;
+#else
+    ucontext_t main_ctx;
+#endif
+    int cur = 0;
+    const std::function<void()> *body = nullptr;
+    long launches = 0;
+};
+inline Sched &S() { static Sched s; return s; }
+
+constexpr size_t kStack = 256 * 1024;
+
+#if EMU_FAST_SWITCH
+inline void yield_to_scheduler() { emu_switch(&S().threads[S().cur].sp, S().main_sp); }
+inline void resume(int t) { emu_switch(&S().main_sp, S().threads[t].sp); }
+inline void thread_entry() {
+    (*S().body)();
+    S().threads[S().cur].state = 3;
+    yield_to_scheduler();
+    abort();                          // an exited thread is never resumed
+}
+inline void prepare(Thread &th) {
+    // stack image that emu_switch "returns" into: six zeroed callee-saved registers, then the entry address in a 16-byte aligned slot
+    uintptr_t top = (reinterpret_cast<uintptr_t>(th.stack) + kStack) & ~static_cast<uintptr_t>(15);
+    void **slot = reinterpret_cast<void **>(top - 16);
+    slot[0] = reinterpret_cast<void *>(&thread_entry);
+    void **sp = slot - 6;
+    for (int i = 0; i < 6; ++i) sp[i] = nullptr;
+    th.sp = sp;
+}
+#else
+inline void yield_to_scheduler() { swapcontext(&S().threads[S().cur].ctx, &S().main_ctx); }
+inline void resume(int t) { swapcontext(&S().main_ctx, &S().threads[t].ctx); }
+inline void thread_entry() {
+    (*S().body)();
+    S().threads[S().cur].state = 3;
+}
+inline void prepare(Thread &th) {
+    getcontext(&th.ctx);
+    th.ctx.uc_stack.ss_sp = th.stack;
+    th.ctx.uc_stack.ss_size = kStack;
+    th.ctx.uc_link = &S().main_ctx;
+    makecontext(&th.ctx, reinterpret_cast<void (*)()>(thread_entry), 0);
+}
+#endif
+
+inline void run_block(int n_threads, const std::function<void()> &fn) {
+    Sched &s = S();
+    if (static_cast<int>(s.threads.size()) < n_threads) {
+        s.threads.resize(n_threads);
+        s.slot.resize(n_threads);
+    }
+    s.body = &fn;
+    for (int t = 0; t < n_threads; ++t) {
+        Thread &th = s.threads[t];
+        if (!th.stack) th.stack = static_cast<char *>(malloc(kStack));
+        prepare(th);
+        th.state = 0;
+    }
+    const dim3 bd = bdim();
+    for (;;) {
+        bool progressed = false, live = false;
+        for (int t = 0; t < n_threads; ++t) {
+            if (s.threads[t].state != 0) continue;
+            s.cur = t;
+            tid() = make_uint3(t % bd.x, (t / bd.x) % bd.y, t / (bd.x * bd.y));
+            resume(t);
+            progressed = true;
+        }
+        // warp rendezvous: every live thread of the warp is waiting
+        for (int w = 0; w * 32 < n_threads; ++w) {
+            int waiting = 0, alive = 0;
+            for (int t = w * 32; t < std::min(n_threads, w * 32 + 32); ++t) {
+                alive += s.threads[t].state != 3;
+                waiting += s.threads[t].state == 2;
+            }
+            if (waiting && waiting == alive) {
+                for (int t = w * 32; t < std::min(n_threads, w * 32 + 32); ++t)
+                    if (s.threads[t].state == 2) s.threads[t].state = 0;
+                progressed = true;
+            }
+        }
+        int at_bar = 0, alive = 0;
+        for (int t = 0; t < n_threads; ++t) {
+            alive += s.threads[t].state != 3;
+            at_bar += s.threads[t].state == 1;
+            live |= s.threads[t].state != 3;
+        }
+        if (at_bar && at_bar == alive) {
+            for (int t = 0; t < n_threads; ++t)
+                if (s.threads[t].state == 1) s.threads[t].state = 0;
+            progressed = true;
+        }
+        if (!live) break;
+        if (!progressed) {
+            fprintf(stderr, "emu: DEADLOCK in block (%u,%u): %d threads alive, %d at __syncthreads, the rest stuck at a warp rendezvous\n", bid().x,
+                    bid().y, alive, at_bar);
+            abort();
+        }
+    }
+}
+
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &fn) {
+    static std::vector<unsigned char> smem;
+    if (smem.size() < smem_bytes + 1024) smem.resize(smem_bytes + 1024);
+    // poison dynamic shared memory so that reads of never-written bytes show up as NaNs / huge values instead of zeros
+    dyn_smem() = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem.data()) + 1023) & ~static_cast<uintptr_t>(1023));
+    gdim() = grid;
+    bdim() = block;
+    S().launches++;
+    const int n_threads = static_cast<int>(block.x * block.y * block.z);
+    for (unsigned z = 0; z < grid.z; ++z)
+        for (unsigned y = 0; y < grid.y; ++y)
+            for (unsigned x = 0; x < grid.x; ++x) {
+                memset(dyn_smem(), 0xFF, smem_bytes);
+                bid() = make_uint3(x, y, z);
+                run_block(n_threads, fn);
+            }
+}
+
+}  // namespace emu
+
+#define threadIdx (emu::tid())
+#define blockIdx (emu::bid())
+#define blockDim (emu::bdim())
+#define gridDim (emu::gdim())
+
+inline void __syncthreads() {
+    emu::S().threads[emu::S().cur].state = 1;
+    emu::yield_to_scheduler();
+}
+inline void __syncwarp(unsigned = 0xffffffffu) {
+    emu::S().threads[emu::S().cur].state = 2;
+    emu::yield_to_scheduler();
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    emu::Sched &s = emu::S();
+    const int me = s.cur;
+    uint64_t bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    s.slot[me] = bits;
+    __syncwarp();
+    const int src = (me & ~31) | ((me ^ lane_mask) & 31);
+    uint64_t got = s.slot[src];
+    __syncwarp();
+    T r;
+    memcpy(&r, &got, sizeof(T));
+    return r;
+}
+template <typename T>
+inline T __ldg(const T *p) { return *p; }
+inline uint32_t __umulhi(uint32_t a, uint32_t b) { return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32); }
+inline float __uint_as_float(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+using std::max;
+using std::min;
+
+namespace sfb {
+
+constexpr int kD = 768;
+
+inline char *err_buf() { static char b[512] = ""; return b; }
+inline void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+}
+inline int num_sms() { return 148; }
+
+#define SFB_CHECK_ARG(cond, ...)          \
+    do {                                  \
+        if (!(cond)) {                    \
+            sfb::set_error(__VA_ARGS__);  \
+            return SFB_E_INVALID;         \
+        }                                 \
+    } while (0)
+#define SFB_CHECK_CUDA(expr)                                  \
+    do {                                                      \
+        cudaError_t e__ = (expr);                             \
+        if (e__ != cudaSuccess) {                             \
+            sfb::set_error("%s failed (emulated)", #expr);    \
+            return SFB_E_CUDA;                                \
+        }                                                     \
+    } while (0)
+#define SFB_CHECK_LAUNCH() SFB_CHECK_CUDA(cudaGetLastError())
+
+// the helpers of the real common.cuh that the N3 kernels use (the PTX-based ones are not needed by them)
+inline float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+inline float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+inline float warp_max(float v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+inline uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    uint32_t u;
+    memcpy(&u, &t, 4);
+    return u;
+}
+inline float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 t;
+    memcpy(&t, &u, 4);
+    return __bfloat1622float2(t);
+}
+
+}  // namespace sfb

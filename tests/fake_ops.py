@@ -19,10 +19,13 @@ from oracle import philox
 
 D = 768
 ROUND_BF16 = False
+REAL_DTYPES = False     # True: bf16 results are real torch.bfloat16 tensors (needed when the stand-ins feed the emulated kernels of tests/emu)
 
 
 def _r(x: torch.Tensor) -> torch.Tensor:
     """bf16 storage: the real kernels hand bf16 tensors around; here they stay fp32 holding bf16-representable values."""
+    if REAL_DTYPES:
+        return x.to(torch.bfloat16)
     return x.to(torch.bfloat16).float() if ROUND_BF16 else x
 
 
@@ -180,12 +183,16 @@ def sync_head_bwd(x, T, ln_w, ln_b, eps, W, dlogits, B):
     return dx.reshape(B * T, D), (dyn * xhat).sum(0), dyn.sum(0), dlogits.t() @ y, dlogits.sum(0)
 
 
-def install(monkeypatch, round_bf16: bool = False):
-    """Route every `ops.<kernel>` used by the sync-module training path to the CPU stand-ins above."""
+ALL = ('require_cuda', 'cast_bf16', 'gemm', 'layernorm', 'sync_tokens', 'sync_head', 'dropout', 'gelu_fwd', 'gelu_bwd',
+       'transpose_bf16', 'colsum', 'layernorm_bwd', 'attention_train_fwd', 'attention_train_bwd', 'sync_head_bwd')
+
+
+def install(monkeypatch, round_bf16: bool = False, names=ALL, real_dtypes: bool = False):
+    """Route `ops.<kernel>` for the given names (default: everything the sync-module training path uses) to the CPU stand-ins above."""
     import sys
     from synchformer_b200 import ops
     me = sys.modules[__name__]
     monkeypatch.setattr(me, 'ROUND_BF16', round_bf16)
-    for name in ('require_cuda', 'cast_bf16', 'gemm', 'layernorm', 'sync_tokens', 'sync_head', 'dropout', 'gelu_fwd', 'gelu_bwd',
-                 'transpose_bf16', 'colsum', 'layernorm_bwd', 'attention_train_fwd', 'attention_train_bwd', 'sync_head_bwd'):
+    monkeypatch.setattr(me, 'REAL_DTYPES', real_dtypes)
+    for name in names:
         monkeypatch.setattr(ops, name, getattr(me, name))

@@ -237,7 +237,7 @@ def test_training_step_gradients_match_oracle_on_golden_features(cuda_device, mo
             assert np.abs(gr.cpu().reshape(-1)[::stride].numpy() - sample).max() <= 5e-2 * np.abs(sample).max() + 2e-3, n
 
 
-def test_training_step_at_five_second_clip_shape(cuda_device, monkeypatch):
+def test_training_step_at_five_second_clip_shape(cuda_device, monkeypatch, check_determinism=True):
     """S = 14 (T = 198), B = 3: B * T = 594 is not a multiple of 8 (padded transposes), 7 row tiles per attention problem."""
     torch.manual_seed(5)
     B, S = 3, 14
@@ -249,6 +249,8 @@ def test_training_step_at_five_second_clip_shape(cuda_device, monkeypatch):
     rloss, rlogits, rgrads = O.sync_train_grads(sd, vf, af, targets, O.train_multipliers(B, 2 + 14 * S, 4242), loss_scale=65536.0)
     assert (logits.cpu() - rlogits).abs().max() < 3e-2
     train_gates.check_grads(grads, rgrads)
+    if not check_determinism:
+        return
     # same seed -> same step, bit for bit (no atomics anywhere); another seed -> another mask
     _, logits2, grads2 = _step(model, vf.to(cuda_device), af.to(cuda_device), targets.to(cuda_device), 4242, monkeypatch, loss_scale=65536.0)
     assert torch.equal(logits, logits2) and all(torch.equal(grads[n], grads2[n]) for n in grads)
