@@ -29,6 +29,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = _lib.SIGNATURES[name]
         lib.emu_launch_count.restype = ctypes.c_long
+        lib.emu_set_schedule.argtypes = [ctypes.c_int, ctypes.c_ulonglong]
         _emu = lib
     return _emu
 

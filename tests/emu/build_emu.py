@@ -97,7 +97,8 @@ def build(force: bool = False) -> str:
     extra = os.path.join(OUT, 'emu_exports.cpp')
     with open(extra, 'w') as fh:
         fh.write('#define EMU_MAIN_TU 1\n#include "common.cuh"\nextern "C" const char *sfb_last_error(void) { return sfb::err_buf(); }\n'
-                 'extern "C" long emu_launch_count(void) { return emu::S().launches; }\n')
+                 'extern "C" long emu_launch_count(void) { return emu::S().launches; }\n'
+                 'extern "C" void emu_set_schedule(int mode, unsigned long long seed) { emu::schedule() = mode; emu::rng() = seed * 2 + 1; }\n')
     cmd = ['g++', '-O2', '-g', '-std=c++17', '-shared', '-fPIC', '-w', '-I', OUT, '-I', CSRC, '-I', CUDA_INC, '-o', LIB] + gen + [extra]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

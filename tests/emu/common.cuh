@@ -101,6 +101,8 @@ inline uint3 &bid() { static uint3 v; return v; }
 inline dim3 &bdim() { static dim3 v; return v; }
 inline dim3 &gdim() { static dim3 v; return v; }
 inline unsigned char *&dyn_smem() { static unsigned char *p = nullptr; return p; }
+inline int &schedule() { static int m = 0; return m; }
+inline uint64_t &rng() { static uint64_t r = 0x9E3779B97F4A7C15ull; return r; }
 
 struct Sched {
     std::vector<Thread> threads;
@@ -166,9 +168,20 @@ inline void run_block(int n_threads, const std::function<void()> &fn) {
         th.state = 0;
     }
     const dim3 bd = bdim();
+    static std::vector<int> order;
+    order.resize(n_threads);
     for (;;) {
         bool progressed = false, live = false;
-        for (int t = 0; t < n_threads; ++t) {
+        // run order of the runnable threads within a pass: forward, reverse or reshuffled every pass.  CUDA promises no order between
+        // barriers, so a correctly synchronised kernel gives bit-identical results under all three (tests run them all).
+        for (int t = 0; t < n_threads; ++t) order[t] = schedule() == 1 ? n_threads - 1 - t : t;
+        if (schedule() == 2)
+            for (int t = n_threads - 1; t > 0; --t) {
+                rng() = rng() * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[t], order[static_cast<int>((rng() >> 33) % static_cast<uint64_t>(t + 1))]);
+            }
+        for (int k = 0; k < n_threads; ++k) {
+            const int t = order[k];
             if (s.threads[t].state != 0) continue;
             s.cur = t;
             tid() = make_uint3(t % bd.x, (t / bd.x) % bd.y, t / (bd.x * bd.y));

@@ -1,0 +1,137 @@
+"""Out-of-bounds check of the N3 kernels on the CPU SIMT emulator: every buffer handed to the C-ABI is placed flush against an
+inaccessible guard page (its END for overruns, then its START for underruns), so a single element read or written outside a buffer
+is a SIGSEGV here instead of an `illegal memory access` on the B200.  Run as a script (a crash must not take pytest down):
+
+    python tests/emu/guarded_run.py        -> prints OK and exits 0
+
+TEST INFRASTRUCTURE ONLY.
+"""
+import ctypes
+import mmap
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from emu import binding  # noqa: E402
+
+PAGE = mmap.PAGESIZE
+libc = ctypes.CDLL(None, use_errno=True)
+libc.mprotect.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+_keep = []
+
+
+class Buf:
+    """n_bytes of read/write memory with PROT_NONE pages on both sides; `front` puts the data right after the leading guard page,
+    otherwise it ends exactly at the trailing guard page."""
+
+    def __init__(self, n_bytes: int, front: bool, fill: int = 0x7F):
+        assert n_bytes % 16 == 0 or not front
+        pages = (n_bytes + PAGE - 1) // PAGE
+        mm = mmap.mmap(-1, (pages + 2) * PAGE)
+        _keep.append(mm)
+        base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+        ctypes.memset(base + PAGE, fill, pages * PAGE)
+        for guard in (base, base + (pages + 1) * PAGE):
+            if libc.mprotect(guard, PAGE, 0) != 0:
+                raise OSError(ctypes.get_errno(), 'mprotect')
+        self.addr = base + PAGE if front else base + (pages + 1) * PAGE - n_bytes
+        self.n_bytes = n_bytes
+
+    def ptr(self):
+        return ctypes.c_void_p(self.addr)
+
+    def np(self, dtype, shape):
+        arr = np.ctypeslib.as_array((ctypes.c_uint8 * self.n_bytes).from_address(self.addr))
+        return arr.view(dtype).reshape(shape)
+
+
+def bf16_bytes(n):
+    return ((n * 2 + 15) // 16) * 16
+
+
+def run(front: bool):
+    lib = binding.load()
+    rng = np.random.default_rng(0)
+
+    def f32(shape, scale=1.0):
+        n = int(np.prod(shape))
+        b = Buf(((n * 4 + 15) // 16) * 16, front)
+        b.np(np.float32, -1)[:n] = rng.standard_normal(n).astype(np.float32) * scale
+        return b
+
+    def bf16(shape, scale=1.0):
+        n = int(np.prod(shape))
+        b = Buf(bf16_bytes(n), front)
+        v = (rng.standard_normal(n).astype(np.float32) * scale).view(np.uint32) >> 16      # truncate to bf16
+        b.np(np.uint16, -1)[:n] = v.astype(np.uint16)
+        return b
+
+    def out(n_bytes):
+        return Buf(((n_bytes + 15) // 16) * 16, front)
+
+    def ok(rc, what):
+        if rc != 0:
+            raise RuntimeError(f'{what}: rc {rc}: {lib.sfb_last_error().decode()}')
+
+    # elementwise
+    n = 333 * 768
+    ok(lib.sfb_dropout(f32(n).ptr(), f32(n).ptr(), out(n * 4).ptr(), 0, n, 0.1, 77, 3, None), 'dropout f32')
+    ok(lib.sfb_dropout(f32(n).ptr(), None, out(n * 2).ptr(), 1, n, 0.1, 77, 3, None), 'dropout bf16')
+    n = 90 * 3072
+    ok(lib.sfb_gelu_fwd(bf16(n).ptr(), out(n * 2).ptr(), n, None), 'gelu fwd')
+    ok(lib.sfb_gelu_bwd(bf16(n).ptr(), bf16(n).ptr(), out(n * 2).ptr(), n, None), 'gelu bwd')
+    # transpose: tails in both dimensions, padded leading dimension
+    for R, C in ((90, 768), (594, 40), (7, 2304), (33, 33 * 8)):
+        ld = (R + 7) // 8 * 8
+        ok(lib.sfb_transpose_bf16(bf16(R * C).ptr(), C, R, C, out(C * ld * 2).ptr(), ld, None), f'transpose {R}x{C}')
+    # column sums: N not a multiple of 64, M not a multiple of 8, both stages
+    for M, N, is_bf in ((90, 768, 1), (1000, 2304, 1), (3, 45 * 768, 0), (513, 34, 0), (1, 768, 0)):
+        src = bf16(M * N) if is_bf else f32(M * N)
+        parts = min(64, (M + 63) // 64)
+        ws = out(parts * N * 4) if parts > 1 else None
+        ok(lib.sfb_colsum(src.ptr(), is_bf, N, M, N, out(N * 4).ptr(), ws.ptr() if ws else None, parts * N if ws else 0, None), f'colsum {M}x{N}')
+    # LayerNorm backward: plain, and with the token gather of the sync sequence (B = 2, S = 3: T = 44)
+    for rows, gather in ((90, None), (1000, None), (2 * 24, (24, 44, 1)), (2 * 18, (18, 44, 26))):
+        group, stride, offset = gather if gather else (rows, rows, 0)
+        n_dy = (rows // group - 1) * stride + offset + group
+        nws = lib.sfb_layernorm_bwd_workspace_floats(rows)
+        dgb = out(2 * 768 * 4)
+        ok(lib.sfb_layernorm_bwd(f32(n_dy * 768).ptr(), 768, group, stride, offset, f32(rows * 768).ptr(), 768, f32(768).ptr(), 1e-5,
+                                 f32(rows * 768).ptr(), 768, 1, ctypes.c_void_p(dgb.addr), ctypes.c_void_p(dgb.addr + 768 * 4), out(nws * 4).ptr(), nws,
+                                 rows, None), f'layernorm bwd {rows}')
+    # attention: T not a multiple of 32 / of 4, both head sizes
+    for B, T, h, d in ((2, 45, 8, 96), (1, 198, 8, 96), (2, 74, 12, 64), (1, 33, 8, 96), (3, 1, 8, 96)):
+        Dm = h * d
+        qkv, o, lse = bf16(B * T * 3 * Dm, 0.5), out(B * T * Dm * 2), out(B * h * T * 4)
+        ok(lib.sfb_attention_train_fwd(qkv.ptr(), o.ptr(), lse.ptr(), B, T, h, d, 0.1, 0.1, 5, 1, None), f'attention fwd T={T}')
+        ok(lib.sfb_attention_train_bwd(qkv.ptr(), o.ptr(), bf16(B * T * Dm).ptr(), lse.ptr(), out(B * h * T * 4).ptr(), out(B * T * 3 * Dm * 2).ptr(), B, T, h, d,
+                                       0.1, 0.1, 5, 1, None), f'attention bwd T={T}')
+    # head
+    for B, T, n_cls in ((2, 44, 21), (5, 198, 2), (1, 30, 64)):
+        ok(lib.sfb_sync_head_bwd(f32(B * T * 768).ptr(), T, f32(768).ptr(), f32(768).ptr(), 1e-5, f32(n_cls * 768, 0.03).ptr(), f32(B * n_cls).ptr(), B, n_cls,
+                                 out(B * T * 768 * 4).ptr(), out(768 * 4).ptr(), out(768 * 4).ptr(), out(n_cls * 768 * 4).ptr(), out(((n_cls * 4 + 15) // 16) * 16).ptr(),
+                                 out(B * 3 * 768 * 4).ptr(), None), f'head bwd B={B}')
+
+
+def selftest_must_crash():
+    """a deliberately short output buffer: the guard page has to turn the overrun into a SIGSEGV"""
+    lib = binding.load()
+    R, C = 64, 64
+    src = Buf(R * C * 2, False)
+    dst = Buf((C - 1) * R * 2, False)                       # one row short
+    lib.sfb_transpose_bf16(src.ptr(), C, R, C, dst.ptr(), R, None)
+
+
+if __name__ == '__main__':
+    if '--selftest' in sys.argv:
+        selftest_must_crash()
+        print('NOT CAUGHT')
+        sys.exit(0)
+    run(front=False)      # overruns
+    run(front=True)       # underruns
+    print('OK')

@@ -55,3 +55,49 @@ def test_emulator_detects_a_missing_barrier_partner():
     finally:
         mp.undo()
     assert lib.emu_launch_count() == before + 2
+
+
+def test_results_do_not_depend_on_the_thread_schedule(monkeypatch):
+    """CUDA guarantees no execution order between barriers.  The emulator runs the runnable threads of a block forward, in reverse, and
+    reshuffled on every scheduler pass: every kernel must return bit-identical results under all schedules (a missing __syncthreads /
+    __syncwarp, or a read of shared memory another thread has not written yet, shows up as a difference or as poison values)."""
+    lib = binding.install(monkeypatch)
+    from synchformer_b200 import ops
+    torch.manual_seed(0)
+    B, T, h, d = 2, 45, 8, 96
+    qkv = (torch.randn((B * T, 3 * h * d)) * 0.8).to(torch.bfloat16)
+    d_out = torch.randn((B * T, h * d)).to(torch.bfloat16)
+    x, dy, gamma = torch.randn((300, 768)), torch.randn((300, 768)), torch.rand(768) + 0.5
+    xh, dl, W = torch.randn((B * T, 768)), torch.randn((B, 21)), torch.randn((21, 768)) * 0.03
+    big = torch.randn((1000, 320)).to(torch.bfloat16)
+
+    def run_all():
+        o, lse = ops.attention_train_fwd(qkv, B, T, h, d, 0.102, 0.1, 5, 2)
+        dqkv = ops.attention_train_bwd(qkv, o, d_out, lse, B, T, h, d, 0.102, 0.1, 5, 2)
+        ln = ops.layernorm_bwd(dy, x, gamma, 1e-5)
+        head = ops.sync_head_bwd(xh, T, gamma, gamma, 1e-5, W, dl, B)
+        return [o, lse, dqkv, *ln, *head, ops.colsum(big), ops.transpose_bf16(big), ops.gelu_bwd(d_out, d_out), ops.dropout(x, 0.3, 9, 1, residual=dy)]
+
+    try:
+        lib.emu_set_schedule(0, 0)
+        base = run_all()
+        assert all(torch.isfinite(t.float()).all() for t in base)
+        for mode, seed in ((1, 0), (2, 1), (2, 2)):
+            lib.emu_set_schedule(mode, seed)
+            for a, b in zip(base, run_all()):
+                assert torch.equal(a, b), f'schedule {mode}/{seed} changed a result'
+    finally:
+        lib.emu_set_schedule(0, 0)
+
+
+def test_no_out_of_bounds_access_under_guard_pages():
+    """tests/emu/guarded_run.py: every buffer flush against a PROT_NONE page, awkward sizes (tails everywhere); a stray access is a SIGSEGV.
+    Runs in a subprocess; the self-test proves the guard pages do catch a one-row overrun."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu', 'guarded_run.py')
+    binding.load()                                           # build once, outside the subprocesses
+    r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith('OK'), (r.returncode, r.stdout[-500:], r.stderr[-2000:])
+    r = subprocess.run([sys.executable, script, '--selftest'], capture_output=True, text=True, timeout=600)
+    assert r.returncode < 0 and 'NOT CAUGHT' not in r.stdout, (r.returncode, r.stdout)
