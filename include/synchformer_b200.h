@@ -202,6 +202,41 @@ int sfb_attention_train_bwd(const void *qkv, const void *out, const void *d_out,
 int sfb_sync_head_bwd(const float *x, int T, const float *ln_w, const float *ln_b, float eps, const float *W, const float *dlogits, int B,
                       int n_cls, float *dx, float *dln_w, float *dln_b, float *dW, float *dbias, float *scratch, void *stream);
 
+/* =========================================================================================================
+ * N1 — backward of the encoders (stage-I contrastive training, open_clip/model.py:474-527, training/train.py:122-154).
+ * Linear layers, LayerNorm, GELU, bias / embedding reductions and the AST attention (74 x 74, fused qkv) reuse the N3 entry points;
+ * the entry points below add what the Motionformer's divided attention and the CLS aggregators need.
+ * ========================================================================================================= */
+
+/* Backward of sfb_attention(desc) for problems whose keys fit in shared memory (Lk + prefix <= ~480): time attention 8 x 9, space
+ * attention 196 x 197 (vit_helper.py:126-146), CLS aggregators 1 x 197 / 1 x 13 (motionformer.py:301-334).  desc is the FORWARD
+ * descriptor (desc->out = the forward output O; q_extra must be NULL); d_out has the strides of out, dq / dk / dv those of q / k / v.
+ * The prefix key / value row is shared by the inner problems of an outer index: its gradient is written per problem to
+ *     dprefix[((inner * n_outer + outer) * n_heads + head) * 2 * head_dim] = { dK[head_dim], dV[head_dim] }     (fp32)
+ * so that one sfb_colsum over the n_inner (or all) problems reduces it deterministically.
+ * stats: sfb_attention_bwd_stats_floats(desc) floats of scratch (row log-sum-exp and dO . O). */
+int64_t sfb_attention_bwd_stats_floats(const sfb_attn_desc *desc);
+int sfb_attention_bwd(const sfb_attn_desc *desc, const void *d_out, void *dq, void *dk, void *dv, float *dprefix, float *stats, void *stream);
+
+/* Backward of the Motionformer CLS query (one query per (outer, head) over all Lk token rows of its outer index, vit_helper.py:124):
+ * writes dq (1 row per outer), and ADDS this query's contribution to dk / dv of every token row - call it after sfb_attention_bwd has
+ * written them.  prefix_grad (n_outer, n_heads, 2, head_dim) fp32, if given, is added to token row 0 (the reduced dprefix of the
+ * divided problems: the CLS token's key / value).  coef: n_outer * n_heads * Lk * 2 floats of scratch.  head_dim 64. */
+int sfb_attention_bwd_global_query(const void *q, int64_t q_outer, const void *k, const void *v, int64_t kv_outer, int64_t kv_row,
+                                   const void *out, const void *d_out, int64_t o_outer, void *dq, void *dk, void *dv,
+                                   const float *prefix_grad, float *coef, int n_outer, int n_heads, int head_dim, int Lk, float scale,
+                                   void *stream);
+
+/* timm DropPath (vit_helper.py:356,371,375; stochastic depth 0 .. 0.2 over the 12 blocks, divided_224_16x4.yaml:59):
+ *     out = (residual ? residual : 0) + in * (keep(seed, site, sample) ? 1 / (1 - p) : 0),  sample = row / rows_per_sample
+ * in / residual (n_rows, 768) fp32, out fp32 or bf16; forward and backward (same role as sfb_dropout). */
+int sfb_droppath(const float *in, const float *residual, void *out, int out_bf16, int64_t n_rows, int rows_per_sample, float p,
+                 uint64_t seed, uint32_t site, void *stream);
+
+/* out[r] (bf16, 768 wide, contiguous) = in[(r / group) * group_stride + offset + r % group] (fp32, row stride ld): the row gather of
+ * sfb_layernorm without the normalisation (patch-token gradients without the CLS rows, fp32 -> bf16 GEMM operands). */
+int sfb_gather_rows_bf16(const float *in, int64_t ld, void *out, int rows, int group, int group_stride, int offset, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,13 @@ SIGNATURES = {
                                         c_float, c_uint64, c_uint32, c_void_p]),
     'sfb_sync_head_bwd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    # N1: backward of the encoders
+    'sfb_attention_bwd_stats_floats': (c_int64, [POINTER(AttnDesc)]),
+    'sfb_attention_bwd': (c_int, [POINTER(AttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sfb_attention_bwd_global_query': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    'sfb_droppath': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_uint64, c_uint32, c_void_p]),
+    'sfb_gather_rows_bf16': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

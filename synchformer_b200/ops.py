@@ -390,3 +390,79 @@ def sync_head_bwd(x: torch.Tensor, T: int, ln_w: torch.Tensor, ln_b: torch.Tenso
                                         _p(db), _p(scratch), _stream(x)), 'sfb_sync_head_bwd')
     _count(2)
     return dx, dln[0], dln[1], dW, db
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N1: backward of the encoders (see include/synchformer_b200.h, "N1")
+# ------------------------------------------------------------------------------------------------------------------
+def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, dq: torch.Tensor, dk: torch.Tensor,
+                  dv: torch.Tensor, *, q_strides, kv_strides, o_strides, n_outer: int, n_inner: int, n_heads: int, head_dim: int, Lq: int, Lk: int,
+                  scale: float, k_prefix: Optional[torch.Tensor] = None, v_prefix: Optional[torch.Tensor] = None, prefix_outer: int = 0):
+    """Backward of `attention(...)` with the same view arguments; d_out is addressed like out, dq / dk / dv like q / k / v.
+    Returns the per-problem prefix gradients (n_inner, n_outer, n_heads, 2, head_dim) fp32 (None without a prefix): sum them over the
+    problems that share the prefix row (colsum)."""
+    require_cuda(q, 'q')
+    for t in (q, k, v, out, d_out, dq, dk, dv):
+        assert t.dtype == torch.bfloat16
+    d = AttnDesc()
+    d.q, d.k, d.v, d.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    d.k_prefix = None if k_prefix is None else k_prefix.data_ptr()
+    d.v_prefix = None if v_prefix is None else v_prefix.data_ptr()
+    d.q_outer, d.q_inner, d.q_row = q_strides
+    d.kv_outer, d.kv_inner, d.kv_row = kv_strides
+    d.o_outer, d.o_inner, d.o_row = o_strides
+    d.prefix_outer = prefix_outer
+    d.n_outer, d.n_inner, d.n_heads, d.head_dim, d.Lq, d.Lk = n_outer, n_inner, n_heads, head_dim, Lq, Lk
+    d.scale, d.impl = scale, 0
+    d.q_extra, d.q_extra_outer, d.extra_partial = None, 0, None
+    lib = _lib.load()
+    stats = torch.empty((lib.sfb_attention_bwd_stats_floats(ctypes.byref(d)),), device=q.device, dtype=torch.float32)
+    dprefix = None if k_prefix is None else torch.empty((n_inner, n_outer, n_heads, 2, head_dim), device=q.device, dtype=torch.float32)
+    check(lib.sfb_attention_bwd(ctypes.byref(d), _p(d_out), _p(dq), _p(dk), _p(dv), _p(dprefix), _p(stats), _stream(q)), 'sfb_attention_bwd')
+    _count(2)
+    return dprefix
+
+
+def attention_bwd_global_query(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, dq: torch.Tensor,
+                               dk: torch.Tensor, dv: torch.Tensor, *, q_outer: int, kv_outer: int, kv_row: int, o_outer: int, n_outer: int, n_heads: int,
+                               head_dim: int, Lk: int, scale: float, prefix_grad: Optional[torch.Tensor] = None):
+    """Backward of the one-query-per-(outer, head) attention over all Lk rows: writes dq, ADDS to dk / dv (and prefix_grad to row 0)."""
+    require_cuda(q, 'q')
+    for t in (q, k, v, out, d_out, dq, dk, dv):
+        assert t.dtype == torch.bfloat16
+    if prefix_grad is not None:
+        assert prefix_grad.dtype == torch.float32 and prefix_grad.is_contiguous() and prefix_grad.numel() == n_outer * n_heads * 2 * head_dim
+    coef = torch.empty((n_outer * n_heads * Lk * 2,), device=q.device, dtype=torch.float32)
+    check(_lib.load().sfb_attention_bwd_global_query(_p(q), q_outer, _p(k), _p(v), kv_outer, kv_row, _p(out), _p(d_out), o_outer, _p(dq), _p(dk), _p(dv),
+                                                     _p(prefix_grad), _p(coef), n_outer, n_heads, head_dim, Lk, scale, _stream(q)),
+          'sfb_attention_bwd_global_query')
+    _count(2)
+
+
+def droppath(x: torch.Tensor, rows_per_sample: int, p: float, seed: int, site: int, *, residual: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None, out_bf16: bool = False) -> torch.Tensor:
+    """out = residual + x * keep(sample) / (1 - p), one decision per `rows_per_sample` consecutive rows; x / residual (rows, 768) fp32."""
+    require_cuda(x, 'x')
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.shape[1] == D and x.shape[0] % rows_per_sample == 0
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == x.shape
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    assert out.is_contiguous() and out.shape == x.shape and out.dtype == (torch.bfloat16 if out_bf16 else torch.float32)
+    check(_lib.load().sfb_droppath(_p(x), _p(residual), _p(out), int(out_bf16), x.shape[0], rows_per_sample, float(p), int(seed), int(site), _stream(x)),
+          'sfb_droppath')
+    _count()
+    return out
+
+
+def gather_rows_bf16(x: torch.Tensor, rows: int, group: Optional[int] = None, group_stride: Optional[int] = None, offset: int = 0) -> torch.Tensor:
+    """(R, 768) fp32 -> (rows, 768) bf16; output row r reads input row (r // group) * group_stride + offset + r % group."""
+    require_cuda(x, 'x')
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == D and x.stride(1) == 1
+    if group is None:
+        group, group_stride = rows, rows
+    assert ((rows - 1) // group) * group_stride + offset + (rows - 1) % group < x.shape[0], 'row gather out of range'
+    out = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().sfb_gather_rows_bf16(_p(x), x.stride(0), _p(out), rows, group, group_stride, offset, _stream(x)), 'sfb_gather_rows_bf16')
+    _count()
+    return out
