@@ -166,13 +166,15 @@ def divided_attention(sd, prefix: str, x: Tensor, mode: str) -> Tensor:
     return _lin(out, sd[prefix + 'proj.weight'], sd[prefix + 'proj.bias'])
 
 
-def video_block(sd, i: int, x: Tensor) -> Tensor:
-    """DividedSpaceTimeBlock.forward, vit_helper.py:364-376: time (norm3) -> space (norm1) -> MLP (norm2)."""
+def video_block(sd, i: int, x: Tensor, drop_path=None) -> Tensor:
+    """DividedSpaceTimeBlock.forward, vit_helper.py:364-376: time (norm3) -> space (norm1) -> MLP (norm2).
+    drop_path = (space multiplier, mlp multiplier), each (BS, 1, 1): timm DropPath in train mode (:371, :375); None = eval."""
     p = f'vfeat_extractor.blocks.{i}.'
+    ms, mm = (1.0, 1.0) if drop_path is None else drop_path
     x = x + divided_attention(sd, p + 'timeattn.', _ln(x, sd[p + 'norm3.weight'], sd[p + 'norm3.bias'], EPS_V), 'time')
-    x = x + divided_attention(sd, p + 'attn.', _ln(x, sd[p + 'norm1.weight'], sd[p + 'norm1.bias'], EPS_V), 'space')
+    x = x + ms * divided_attention(sd, p + 'attn.', _ln(x, sd[p + 'norm1.weight'], sd[p + 'norm1.bias'], EPS_V), 'space')
     hdn = _gelu(_lin(_ln(x, sd[p + 'norm2.weight'], sd[p + 'norm2.bias'], EPS_V), sd[p + 'mlp.fc1.weight'], sd[p + 'mlp.fc1.bias']))
-    return x + _lin(hdn, sd[p + 'mlp.fc2.weight'], sd[p + 'mlp.fc2.bias'])
+    return x + mm * _lin(hdn, sd[p + 'mlp.fc2.weight'], sd[p + 'mlp.fc2.bias'])
 
 
 def cls_aggregator(sd, prefix: str, x: Tensor) -> Tensor:
@@ -403,3 +405,63 @@ def sync_train_grads(sd, vfeat: Tensor, afeat: Tensor, targets: Tensor, mult: Op
         loss = F.cross_entropy(logits, targets)
         grads = torch.autograd.grad(loss * loss_scale, [leaves[k] for k in names])
     return loss.detach(), logits.detach(), {k: g for k, g in zip(names, grads)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# N1: stage-I training step of the two encoders - AVCLIP.forward / compute_loss
+# (train_clip_src/open_clip/model.py:474-527) with both towers in train mode.  The only stochastic layer is the Motionformer's
+# DropPath (rate 0.2 i / 11 in block i, divided_224_16x4.yaml:59, video_model_builder.py:86-87); its per-segment multipliers are
+# explicit inputs here.  Pinned by tests/golden/encoders_train_b1s2.npz (the reference towers with the same multipliers injected in
+# place of their DropPath instances; tests/golden/make_golden_encoders_train.py).
+# ----------------------------------------------------------------------------------------------------------
+DROP_PATH_RATE = 0.2
+
+
+def drop_path_multipliers(n_segments: int, seed: int, rate: float = DROP_PATH_RATE) -> dict:
+    """{block i: (space (n, 1, 1), mlp (n, 1, 1))}: what the CUDA kernels apply for `seed` (sites 2 i and 2 i + 1, one decision per
+    segment, csrc/philox.cuh)."""
+    from . import philox
+    out = {}
+    for i in range(V_DEPTH):
+        p = rate * i / (V_DEPTH - 1)
+        out[i] = tuple(torch.from_numpy(philox.dropout_multiplier((n_segments,), p, seed, 2 * i + k)).reshape(n_segments, 1, 1) for k in (0, 1))
+    return out
+
+
+def encoder_features_train(sd, vis: Tensor, aud: Tensor, drop_path: Optional[dict] = None):
+    """Differentiable towers on the given leaves (no cast, no detach): vis (B, S, 16, 3, 224, 224), aud (B, S, 1, 128, 66) ->
+    ((B, S, 8, 768), (B, S, 6, 768))."""
+    B, S = vis.shape[:2]
+    x = video_patch_embed(sd, vis.reshape(B * S, *vis.shape[2:]))
+    for i in range(V_DEPTH):
+        x = video_block(sd, i, x, None if drop_path is None else drop_path[i])
+    x = _ln(x[:, 1:], sd['vfeat_extractor.norm.weight'], sd['vfeat_extractor.norm.bias'], EPS_V)
+    v = cls_aggregator(sd, 'vfeat_extractor.spatial_attn_agg.', x.reshape(B * S * V_FRAMES, V_SPACE, D)).reshape(B, S, V_FRAMES, D)
+    y = audio_patch_embed(sd, aud.reshape(B * S, 128, 66))
+    for i in range(A_DEPTH):
+        y = ast_layer(sd, i, y)
+    y = _ln(y, sd['afeat_extractor.ast.layernorm.weight'], sd['afeat_extractor.ast.layernorm.bias'], EPS_A)
+    y = y[:, 2:].reshape(B * S, A_F, A_T, D).permute(0, 2, 1, 3).reshape(B * S * A_T, A_F, D)
+    a = cls_aggregator(sd, 'afeat_extractor.freq_attn_agg.', y).reshape(B, S, A_T, D)
+    return v, a
+
+
+def contrastive_loss(vfeat: Tensor, afeat: Tensor, logit_scale) -> Tensor:
+    """AVCLIP.compute_loss / _loss (open_clip/model.py:507-527) on time-pooled (B, S, 8|6, 768) features: mean over the time tokens
+    (AveragePooling, motionformer.py:395-409), flatten (B S), L2-normalise, symmetric soft-target cross-entropy with identity targets."""
+    v = F.normalize(vfeat.mean(2).reshape(-1, D), dim=-1)
+    a = F.normalize(afeat.mean(2).reshape(-1, D), dim=-1)
+    sim_v2a, sim_a2v = v @ a.mT / logit_scale, a @ v.mT / logit_scale
+    tgt = torch.eye(*sim_v2a.shape, dtype=sim_v2a.dtype)
+    return (F.cross_entropy(sim_v2a, tgt) + F.cross_entropy(sim_a2v, tgt)) / 2
+
+
+def encoders_train_grads(sd, vis: Tensor, aud: Tensor, drop_path: Optional[dict] = None, logit_scale: float = 0.07, dtype=torch.float32):
+    """-> (loss, vfeat, afeat, {name: d loss / d param}) for every extractor parameter that takes part in the forward."""
+    names = [k for k in sd if k.split('.')[0] in ('vfeat_extractor', 'afeat_extractor') and '.patch_embed.proj.' not in k]
+    leaves = {k: sd[k].detach().to(dtype).clone().requires_grad_(True) for k in names}
+    with torch.enable_grad():
+        v, a = encoder_features_train(leaves, vis.to(dtype), aud.to(dtype), drop_path)
+        loss = contrastive_loss(v, a, logit_scale)
+        grads = torch.autograd.grad(loss, [leaves[k] for k in names])
+    return loss.detach(), v.detach(), a.detach(), dict(zip(names, grads))

@@ -289,12 +289,13 @@ def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return dx
 
 
-def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
-    """(R, C) bf16 (row stride may exceed C) -> (C, R) bf16 view of a (C, ceil8(R)) buffer whose padding columns are zero."""
+def transpose_bf16(x: torch.Tensor, pad_to: int = 8) -> torch.Tensor:
+    """(R, C) bf16 (row stride may exceed C) -> (C, ceil(R / pad_to) * pad_to) bf16 whose padding columns are zero (pad_to % 8 == 0:
+    the result is used as a GEMM operand with K = its width)."""
     require_cuda(x, 'x')
-    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and pad_to % 8 == 0
     R, C = x.shape
-    ld = (R + 7) // 8 * 8
+    ld = (R + pad_to - 1) // pad_to * pad_to
     out = torch.empty((C, ld), device=x.device, dtype=torch.bfloat16)
     check(_lib.load().sfb_transpose_bf16(_p(x), x.stride(0), R, C, _p(out), ld, _stream(x)), 'sfb_transpose_bf16')
     _count()
@@ -395,6 +396,11 @@ def sync_head_bwd(x: torch.Tensor, T: int, ln_w: torch.Tensor, ln_b: torch.Tenso
 # ------------------------------------------------------------------------------------------------------------------
 # N1: backward of the encoders (see include/synchformer_b200.h, "N1")
 # ------------------------------------------------------------------------------------------------------------------
+def empty_bf16(shape, device) -> torch.Tensor:
+    """activation buffer (one place to allocate them, so tests can swap the storage type of the stand-ins)"""
+    return torch.empty(shape, device=device, dtype=torch.bfloat16)
+
+
 def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, dq: torch.Tensor, dk: torch.Tensor,
                   dv: torch.Tensor, *, q_strides, kv_strides, o_strides, n_outer: int, n_inner: int, n_heads: int, head_dim: int, Lq: int, Lk: int,
                   scale: float, k_prefix: Optional[torch.Tensor] = None, v_prefix: Optional[torch.Tensor] = None, prefix_outer: int = 0):

@@ -51,7 +51,8 @@ def draw_seed() -> int:
 
 
 def _t(x: torch.Tensor) -> torch.Tensor:
-    return ops.transpose_bf16(x)
+    """transposed GEMM operand; a reduction dimension shorter than one 64-wide k-block is zero-padded up to it"""
+    return ops.transpose_bf16(x, 64 if x.shape[0] < 64 else 8)
 
 
 class _LinearFn(torch.autograd.Function):
