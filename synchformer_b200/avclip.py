@@ -6,7 +6,8 @@ forward pass in eval / no_grad: encoders with `agg_time_module='AveragePooling'`
 identity targets.  Inputs come in the STAGE-I layouts: rgb (B, S, C=3, T=16, H, W), audio (B, S, T=66, F=128)
 (segment_avclip.yaml:208-211).  The encoders are the kernel-backed `MotionFormer` / `AST` of model.py; the 128 x 128 similarity tail is
 three tiny torch ops (normalise, matmul, cross_entropy) - plumbing next to 52 TFLOP of encoder work.
-The backward of the encoders (the actual stage-I training step) is out of scope for this round.
+In train mode (with autograd on) the towers take their differentiable path (train_encoders.py, SURVEY.md §8f N1: DropPath + hand-written
+backward), so `out['losses']['segment_contrastive_loss'].backward()` fills the gradients of both encoders and of `logit_scale`.
 """
 import torch
 import torch.nn.functional as F
@@ -36,9 +37,12 @@ class AVCLIP(nn.Module):
             v, a = F.normalize(v, dim=-1), F.normalize(a, dim=-1)
         return v, a
 
-    @torch.no_grad()
     def forward(self, vis: torch.Tensor, aud: torch.Tensor, alpha: float = 0.0, for_loop: bool = False, world_size: int = 1):
         assert alpha == 0.0, f'alpha={alpha} not supported yet'          # same assertion as the reference (:489)
+        with torch.set_grad_enabled(torch.is_grad_enabled() and self.training):     # eval: inference kernels, nothing is recorded
+            return self._forward(vis, aud)
+
+    def _forward(self, vis: torch.Tensor, aud: torch.Tensor):
         scale = self.logit_scale.clamp(self.clamp_scale_min, self.clamp_scale_max)
         vfeat, afeat = self.encode_streams(vis, aud)
         sim_v2a = vfeat @ afeat.mT / self.logit_scale                     # compute_loss :507-513

@@ -10,8 +10,9 @@ Parameters are ordinary fp32 `nn.Parameter`s under the reference's names (so `lo
 keeps three matrices) are cached per device and refreshed when a parameter's version counter changes.
 
 All arithmetic runs in the CUDA kernels of `libsynchformer_b200.so` (see ops.py); PyTorch only owns memory and
-streams.  The feature extractors are inference-only (frozen, as configs/sync.yaml trains them); the synchronisation module
-(vproj / aproj / transformer) also trains: in train mode its forward applies dropout and is differentiable (train.py).
+streams.  Everything also trains: in train mode the synchronisation module (vproj / aproj / transformer) applies dropout and is
+differentiable (train.py), and so are the two feature extractors when they have trainable parameters
+(train_encoders.py, §8f N1); frozen / eval towers, as configs/sync.yaml uses them, keep the inference path.
 """
 import logging
 import math
@@ -20,7 +21,7 @@ from typing import Any, Dict, Mapping, Optional
 import torch
 from torch import nn
 
-from . import ops, train
+from . import ops, train, train_encoders
 from .schema import D, state_dict_schema
 
 EPS_V, EPS_A, EPS_S = 1e-6, 1e-12, 1e-5
@@ -60,6 +61,12 @@ def _init_reference_like(module: nn.Module):
                 p.normal_(0.0, 1.0)                       # torch.randn in sync_model.py:129-130, transformer.py:126
             else:
                 nn.init.trunc_normal_(p, std=0.02)
+
+
+def _tower_trains(m: nn.Module) -> bool:
+    """A feature extractor takes the differentiable path iff it is in train mode, autograd is on and it has trainable parameters
+    (stage I, or stage II with `is_trainable: True`); frozen / eval towers keep the inference path."""
+    return m.training and torch.is_grad_enabled() and any(p.requires_grad for n, p in m.named_parameters() if not n.startswith('patch_embed.'))
 
 
 class _KernelModule(nn.Module):
@@ -238,6 +245,8 @@ class MotionFormer(_KernelModule):
         if vis.dim() != 6 or tuple(vis.shape[2:]) != (16, 3, 224, 224):
             raise ValueError(f'expected video of shape (B, S, 16, 3, 224, 224), got {tuple(vis.shape)}')
         B, S = vis.shape[:2]
+        if _tower_trains(self):                                  # differentiable forward + hand-written backward
+            return train_encoders.motionformer_features(self, vis)
         P, W = self.weights()
         flat = vis.contiguous().view(B * S, 16, 3, 224, 224)
         outs = [self._encode_chunk(flat[s:s + self.max_segments_per_pass], P, W) for s in range(0, B * S, self.max_segments_per_pass)]
@@ -296,6 +305,8 @@ class AST(_KernelModule):
             raise ValueError(f'expected spectrogram of shape (B, S, 128, 66), got {tuple(spec.shape)}')
         B, S = spec.shape[:2]
         n = B * S
+        if _tower_trains(self):
+            return train_encoders.ast_features(self, spec)
         P, W = self.weights()
         e = 'ast.embeddings.'
         a = ops.im2col_ast(spec.float().contiguous().view(n, 128, 66))
@@ -493,12 +504,6 @@ class Synchformer(nn.Module):
     def forward(self, vis: torch.Tensor, aud: torch.Tensor, targets: torch.Tensor = None, for_loop=False, vis_mask: torch.Tensor = None,
                 aud_mask: torch.Tensor = None, loss_fn=None):
         """vis (B, S, Tv=16, C=3, H=224, W=224), aud (B, S, 1, F=128, Ta=66) -> (loss | None, logits (B, n_cls))."""
-        if self.training and torch.is_grad_enabled() and any(
-                p.requires_grad for m in (self.vfeat_extractor, self.afeat_extractor) for n, p in m.named_parameters()
-                if not n.startswith('patch_embed.')):
-            raise NotImplementedError('the backward of the feature extractors is not implemented (SURVEY.md §8f N1): freeze them as '
-                                      'configs/sync.yaml:8,20 (is_trainable: False) + scripts/train_utils.py:199-204 do, i.e. '
-                                      'requires_grad_(False) and .eval() on vfeat_extractor / afeat_extractor')
         vis = self.extract_vfeats(vis, for_loop, vis_mask=vis_mask)
         aud = self.extract_afeats(aud, for_loop, aud_mask=aud_mask)
         v, a = self.project(vis, aud)
@@ -536,6 +541,8 @@ class Synchformer(nn.Module):
     def extract_vfeats(self, vis, for_loop=False, vis_mask=None):
         if vis_mask is not None:
             raise NotImplementedError('vis_mask is not supported (no caller in the reference passes it)')
+        if _tower_trains(self.vfeat_extractor):               # is_trainable: True -> gradients flow into the tower (train_encoders.py)
+            return self.vfeat_extractor.encode(vis)
         with torch.no_grad():
             return self.vfeat_extractor.encode(vis)           # for_loop only trades memory for speed in the reference; results are identical
 
@@ -543,6 +550,8 @@ class Synchformer(nn.Module):
         if aud_mask is not None:
             raise NotImplementedError('aud_mask is not supported (no caller in the reference passes it)')
         B, S, _, Fa, Ta = aud.shape
+        if _tower_trains(self.afeat_extractor):
+            return self.afeat_extractor.encode(aud.view(B, S, Fa, Ta))
         with torch.no_grad():
             return self.afeat_extractor.encode(aud.view(B, S, Fa, Ta))
 

@@ -26,7 +26,7 @@ def cuda_device():
         # tests/fake_ops.py (shapes, tolerances, oracle plumbing), so that on the GPU box only the kernels themselves can fail
         import fake_ops
         mp = pytest.MonkeyPatch()
-        fake_ops.install(mp, round_bf16=True)
+        fake_ops.install(mp, round_bf16=True, names=fake_ops.ALL + fake_ops.ENCODER_FWD + fake_ops.N1_BWD)
         return torch.device('cpu')
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')

@@ -111,6 +111,56 @@ def run(front: bool):
         ok(lib.sfb_attention_train_fwd(qkv.ptr(), o.ptr(), lse.ptr(), B, T, h, d, 0.1, 0.1, 5, 1, None), f'attention fwd T={T}')
         ok(lib.sfb_attention_train_bwd(qkv.ptr(), o.ptr(), bf16(B * T * Dm).ptr(), lse.ptr(), out(B * h * T * 4).ptr(), out(B * T * 3 * Dm * 2).ptr(), B, T, h, d,
                                        0.1, 0.1, 5, 1, None), f'attention bwd T={T}')
+    # N1: strided attention backward with a shared prefix row (Motionformer layouts on one segment), global query, DropPath, gather
+    from synchformer_b200._lib import AttnDesc
+    D, TOK, h, d = 768, 1569, 12, 64
+    row, seg = 3 * D, TOK * 3 * D
+    for n, mode in ((1, 'time'), (1, 'space')):
+        qkv, att, d_o = bf16(n * TOK * 3 * D, 0.5), bf16(n * TOK * D), bf16(n * TOK * D)
+        dqkv = out(n * TOK * 3 * D * 2)
+        ctypes.memset(dqkv.addr, 0, dqkv.n_bytes)
+        desc = AttnDesc()
+        e = 2                                                       # bytes per element
+        desc.q, desc.k, desc.v, desc.out = qkv.addr + row * e, qkv.addr + (row + D) * e, qkv.addr + (row + 2 * D) * e, att.addr + D * e
+        desc.k_prefix, desc.v_prefix, desc.prefix_outer = qkv.addr + D * e, qkv.addr + 2 * D * e, seg
+        if mode == 'time':
+            st, so, desc.n_inner, desc.Lq, desc.Lk = (seg, row, 196 * row), (TOK * D, D, 196 * D), 196, 8, 8
+        else:
+            st, so, desc.n_inner, desc.Lq, desc.Lk = (seg, 196 * row, row), (TOK * D, 196 * D, D), 8, 196, 196
+        desc.q_outer, desc.q_inner, desc.q_row = st
+        desc.kv_outer, desc.kv_inner, desc.kv_row = st
+        desc.o_outer, desc.o_inner, desc.o_row = so
+        desc.n_outer, desc.n_heads, desc.head_dim, desc.scale, desc.impl = n, h, d, 0.125, 0
+        desc.q_extra, desc.q_extra_outer, desc.extra_partial = None, 0, None
+        n_stats = lib.sfb_attention_bwd_stats_floats(ctypes.byref(desc))
+        part = out(desc.n_inner * n * h * 2 * d * 4)
+        ok(lib.sfb_attention_bwd(ctypes.byref(desc), ctypes.c_void_p(d_o.addr + D * e), ctypes.c_void_p(dqkv.addr + row * e),
+                                 ctypes.c_void_p(dqkv.addr + (row + D) * e), ctypes.c_void_p(dqkv.addr + (row + 2 * D) * e), part.ptr(),
+                                 out(n_stats * 4).ptr(), None), f'attention bwd {mode}')
+        pg = out(n * h * 2 * d * 4)
+        ok(lib.sfb_colsum(part.ptr(), 0, n * h * 2 * d, desc.n_inner, n * h * 2 * d, pg.ptr(), None, 0, None), 'prefix colsum')
+        ok(lib.sfb_attention_bwd_global_query(qkv.ptr(), seg, ctypes.c_void_p(qkv.addr + D * e), ctypes.c_void_p(qkv.addr + 2 * D * e), seg, row, att.ptr(),
+                                              d_o.ptr(), TOK * D, dqkv.ptr(), ctypes.c_void_p(dqkv.addr + D * e), ctypes.c_void_p(dqkv.addr + 2 * D * e),
+                                              pg.ptr(), out(n * h * TOK * 2 * 4).ptr(), n, h, d, TOK, 0.125, None), f'global query {mode}')
+    # aggregator-style: one query per group, strided keys (AST frequency aggregator: 6 groups of 12 keys in 72 rows), shared prefix
+    n = 3
+    kv, ao, dao, qrep = bf16(n * 72 * 1536, 0.5), bf16(n * 6 * D), bf16(n * 6 * D), bf16(n * 6 * D, 0.5)
+    cls_qkv = bf16(3 * D, 0.5)
+    desc = AttnDesc()
+    desc.q, desc.k, desc.v, desc.out = qrep.addr, kv.addr, kv.addr + D * 2, ao.addr
+    desc.k_prefix, desc.v_prefix, desc.prefix_outer = cls_qkv.addr + D * 2, cls_qkv.addr + 2 * D * 2, 0
+    desc.q_outer, desc.q_inner, desc.q_row = 6 * D, D, D
+    desc.kv_outer, desc.kv_inner, desc.kv_row = 72 * 1536, 1536, 6 * 1536
+    desc.o_outer, desc.o_inner, desc.o_row = 6 * D, D, D
+    desc.n_outer, desc.n_inner, desc.n_heads, desc.head_dim, desc.Lq, desc.Lk, desc.scale, desc.impl = n, 6, 12, 64, 1, 12, 0.125, 0
+    desc.q_extra, desc.q_extra_outer, desc.extra_partial = None, 0, None
+    dkv = out(n * 72 * 1536 * 2)
+    ok(lib.sfb_attention_bwd(ctypes.byref(desc), dao.ptr(), out(n * 6 * D * 2).ptr(), dkv.ptr(), ctypes.c_void_p(dkv.addr + D * 2), out(6 * n * 12 * 2 * 64 * 4).ptr(),
+                             out(lib.sfb_attention_bwd_stats_floats(ctypes.byref(desc)) * 4).ptr(), None), 'attention bwd aggregator')
+    rows = 4 * 1569
+    ok(lib.sfb_droppath(f32(rows * 768).ptr(), f32(rows * 768).ptr(), out(rows * 768 * 4).ptr(), 0, rows, 1569, 0.3, 5, 2, None), 'droppath')
+    ok(lib.sfb_droppath(f32(rows * 768).ptr(), None, out(rows * 768 * 2).ptr(), 1, rows, 1569, 0.3, 5, 2, None), 'droppath bf16')
+    ok(lib.sfb_gather_rows_bf16(f32(rows * 768).ptr(), 768, out(4 * 1568 * 768 * 2).ptr(), 4 * 1568, 1568, 1569, 1, None), 'gather rows')
     # head
     for B, T, n_cls in ((2, 44, 21), (5, 198, 2), (1, 30, 64)):
         ok(lib.sfb_sync_head_bwd(f32(B * T * 768).ptr(), T, f32(768).ptr(), f32(768).ptr(), 1e-5, f32(n_cls * 768, 0.03).ptr(), f32(B * n_cls).ptr(), B, n_cls,

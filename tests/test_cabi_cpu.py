@@ -97,3 +97,38 @@ def test_training_entry_points_validate_then_reach_the_launch():
     assert bad == [-1] * len(bad), bad
     assert lib.sfb_attention_train_fwd(P(0), P(1), P(2), 1, 600, 8, 96, 0.1, 0.0, 0, 0, None) == -3   # T too long for shared memory
     assert b'shared memory' in lib.sfb_last_error()
+
+
+def test_encoder_backward_entry_points_validate_then_reach_the_launch():
+    """N1 entry points, same idea as above: well-formed calls fail only at the launch (-2) on a box without a GPU, malformed ones earlier."""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('would launch kernels on fake addresses')
+    lib = _lib.load()
+    A = 0x100000
+    d = _lib.AttnDesc()
+    D, TOK = 768, 1569
+    row, seg = 3 * D, TOK * 3 * D
+    d.q, d.k, d.v, d.out = A + row * 2, A + (row + D) * 2, A + (row + 2 * D) * 2, 2 * A
+    d.k_prefix, d.v_prefix, d.prefix_outer = A + D * 2, A + 2 * D * 2, seg
+    d.q_outer, d.q_inner, d.q_row = seg, 196 * row, row
+    d.kv_outer, d.kv_inner, d.kv_row = seg, 196 * row, row
+    d.o_outer, d.o_inner, d.o_row = TOK * D, 196 * D, D
+    d.n_outer, d.n_inner, d.n_heads, d.head_dim, d.Lq, d.Lk, d.scale = 2, 8, 12, 64, 196, 196, 0.125
+    P = lambda k: ctypes.c_void_p(A * (k + 3))
+    assert lib.sfb_attention_bwd_stats_floats(ctypes.byref(d)) == 2 * 8 * 12 * 196 * 2
+    assert lib.sfb_attention_bwd(ctypes.byref(d), P(0), P(1), P(2), P(3), P(4), P(5), None) == -2, lib.sfb_last_error()
+    assert lib.sfb_attention_bwd(ctypes.byref(d), P(0), P(1), P(2), P(3), None, P(5), None) == -1       # prefix without dprefix
+    d.Lk = 2000
+    assert lib.sfb_attention_bwd(ctypes.byref(d), P(0), P(1), P(2), P(3), P(4), P(5), None) == -3       # does not fit in shared memory
+    d.Lk, d.kv_row = 196, row + 1
+    assert lib.sfb_attention_bwd(ctypes.byref(d), P(0), P(1), P(2), P(3), P(4), P(5), None) == -1       # unaligned rows
+    assert lib.sfb_attention_bwd_global_query(P(0), seg, P(1), P(2), seg, row, P(3), P(4), TOK * D, P(5), P(6), P(7), P(8), P(9), 2, 12, 64, TOK, 0.125,
+                                              None) == -2
+    assert lib.sfb_attention_bwd_global_query(P(0), seg, P(1), P(2), seg, row, P(3), P(4), TOK * D, P(5), P(6), P(7), None, P(9), 2, 12, 96, TOK, 0.125,
+                                              None) == -1
+    assert lib.sfb_droppath(P(0), P(1), P(2), 0, 4 * 1569, 1569, 0.2, 7, 3, None) == -2
+    assert lib.sfb_droppath(P(0), None, P(2), 1, 4 * 1569 + 1, 1569, 0.2, 7, 3, None) == -1             # rows not a multiple of the sample size
+    assert lib.sfb_gather_rows_bf16(P(0), 768, P(1), 2 * 1568, 1568, 1569, 1, None) == -2
+    assert lib.sfb_gather_rows_bf16(P(0), 700, P(1), 2 * 1568, 1568, 1569, 1, None) == -1

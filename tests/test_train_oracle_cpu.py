@@ -159,13 +159,6 @@ def test_eval_mode_without_grad_does_not_take_the_training_path(setup, monkeypat
     assert not called
 
 
-def test_training_with_trainable_extractors_is_refused(setup):
-    model = M.build_synchformer(n_segments=setup['S'])
-    model.train()
-    with pytest.raises(NotImplementedError, match='feature extractors'):
-        model(torch.zeros(1, setup['S'], 16, 3, 224, 224), torch.zeros(1, setup['S'], 1, 128, 66), torch.tensor([0]))
-
-
 def test_tok_pdrop_is_refused(setup, monkeypatch):
     fake_ops.install(monkeypatch)
     model = _train_model(setup, 0.1)
