@@ -202,6 +202,22 @@ int sfb_attention_train_bwd(const void *qkv, const void *out, const void *d_out,
 int sfb_sync_head_bwd(const float *x, int T, const float *ln_w, const float *ln_b, float eps, const float *W, const float *dlogits, int B,
                       int n_cls, float *dx, float *dln_w, float *dln_b, float *dW, float *dbias, float *scratch, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * N3, optimiser side (scripts/train_utils.py:373-386: scaler.unscale_ -> clip_grad_norm_ -> Adam step; sync_model.py:91-99 loss).
+ * A tensor list is described by a device table of n_tensors entries { float *param, const float *grad, float *exp_avg,
+ * float *exp_avg_sq, int64_t n } (40 bytes each) plus, per chunk of sfb_optim_chunk_elems() elements, the index of its tensor
+ * (chunk_tensor) and its first element (chunk_start).  All tensors fp32, contiguous. */
+/* loss[0] = mean_b( logsumexp(logits[b]) - logits[b, targets[b]] ),  dlogits = (softmax(logits) - onehot(targets)) / B;  row_loss: B floats scratch */
+int sfb_cross_entropy(const float *logits, const int64_t *targets, int B, int C, float *loss, float *dlogits, float *row_loss, void *stream);
+int sfb_optim_chunk_elems(void);
+/* sqnorm[0] = sum over all listed gradients of g^2 (partial: n_chunks floats scratch; fixed summation order) */
+int sfb_grad_sqnorm(const void *table, const int32_t *chunk_tensor, const int64_t *chunk_start, int n_chunks, float *partial, float *sqnorm, void *stream);
+/* torch.optim.Adam step (L2 weight decay, no amsgrad) on every listed tensor in one launch.  With norm = sqrt(sqnorm[0]) * inv_scale:
+ * a non-finite norm skips the step and sets found_inf[0] = 1 (else 0); g = grad * inv_scale * min(1, max_norm / (norm + 1e-6))
+ * (max_norm <= 0: no clipping).  step_count[0] (device, float) holds the number of completed steps and advances only if not skipped. */
+int sfb_adam_step(const void *table, const int32_t *chunk_tensor, const int64_t *chunk_start, int n_chunks, const float *sqnorm, float *found_inf,
+                  float *step_count, float lr, float beta1, float beta2, float eps, float weight_decay, float inv_scale, float max_norm, void *stream);
+
 /* =========================================================================================================
  * N1 — backward of the encoders (stage-I contrastive training, open_clip/model.py:474-527, training/train.py:122-154).
  * Linear layers, LayerNorm, GELU, bias / embedding reductions and the AST attention (74 x 74, fused qkv) reuse the N3 entry points;

@@ -68,6 +68,11 @@ SIGNATURES = {
                                         c_float, c_uint64, c_uint32, c_void_p]),
     'sfb_sync_head_bwd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sfb_cross_entropy': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sfb_optim_chunk_elems': (c_int, []),
+    'sfb_grad_sqnorm': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'sfb_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
+                              c_float, c_void_p]),
     # N1: backward of the encoders
     'sfb_attention_bwd_stats_floats': (c_int64, [POINTER(AttnDesc)]),
     'sfb_attention_bwd': (c_int, [POINTER(AttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -559,7 +559,11 @@ class Synchformer(nn.Module):
         loss = None
         if targets is not None:
             if loss_fn is None or loss_fn == 'cross_entropy':
-                loss = torch.nn.functional.cross_entropy(logits, targets)
+                if logits.is_cuda and logits.requires_grad and targets.dim() == 1 and targets.dtype == torch.int64:
+                    from . import optim                          # training step: loss and d loss / d logits in one launch
+                    loss = optim.cross_entropy(logits, targets)
+                else:
+                    loss = torch.nn.functional.cross_entropy(logits, targets)
             else:
                 raise NotImplementedError(f'Loss {loss_fn} not implemented')
         return loss

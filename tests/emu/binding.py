@@ -14,7 +14,8 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 EMULATED = ('sfb_dropout', 'sfb_gelu_fwd', 'sfb_gelu_bwd', 'sfb_transpose_bf16', 'sfb_colsum', 'sfb_layernorm_bwd_workspace_floats',
             'sfb_layernorm_bwd', 'sfb_attention_train_fwd', 'sfb_attention_train_bwd', 'sfb_sync_head_bwd', 'sfb_last_error',
-            'sfb_attention_bwd_stats_floats', 'sfb_attention_bwd', 'sfb_attention_bwd_global_query', 'sfb_droppath', 'sfb_gather_rows_bf16')
+            'sfb_attention_bwd_stats_floats', 'sfb_attention_bwd', 'sfb_attention_bwd_global_query', 'sfb_droppath', 'sfb_gather_rows_bf16',
+            'sfb_cross_entropy', 'sfb_optim_chunk_elems', 'sfb_grad_sqnorm', 'sfb_adam_step')
 STAND_INS = ('require_cuda', 'cast_bf16', 'gemm', 'layernorm', 'sync_tokens', 'sync_head', 'im2col_video', 'video_tokens', 'im2col_ast',
              'ast_tokens', 'attention')
 

@@ -16,7 +16,7 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(REPO, 'synchformer_b200', 'csrc')
 OUT = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT, 'libsfb_emu.so')
-SOURCES = ['train.cu', 'attention_train.cu', 'attention_bwd.cu']
+SOURCES = ['train.cu', 'attention_train.cu', 'attention_bwd.cu', 'optim.cu']
 CUDA_INC = os.environ.get('CUDA_INC', '/usr/local/cuda/include')
 
 

@@ -101,3 +101,6 @@ def test_no_out_of_bounds_access_under_guard_pages():
     assert r.returncode == 0 and r.stdout.strip().endswith('OK'), (r.returncode, r.stdout[-500:], r.stderr[-2000:])
     r = subprocess.run([sys.executable, script, '--selftest'], capture_output=True, text=True, timeout=600)
     assert r.returncode < 0 and 'NOT CAUGHT' not in r.stdout, (r.returncode, r.stdout)
+
+
+test_fused_cross_entropy_and_adam = G.test_fused_cross_entropy_and_adam

@@ -305,3 +305,53 @@ def test_full_forward_in_train_mode_with_frozen_extractors_and_optimizer_steps(c
     with torch.no_grad():
         _, lg = model(vis, aud)
     assert torch.isfinite(lg).all()
+
+
+def test_fused_cross_entropy_and_adam(cuda_device):
+    """sfb_cross_entropy vs F.cross_entropy (+ autograd); FusedAdam vs torch.optim.Adam over several steps, plain and with the fused
+    unscale + clip_grad_norm_ + skip-on-inf path against GradScaler-style reference arithmetic."""
+    from synchformer_b200 import optim
+    dev = cuda_device
+    torch.manual_seed(0)
+    logits = (torch.randn(37, 21) * 3).to(dev).requires_grad_(True)
+    targets = torch.randint(0, 21, (37,)).to(dev)
+    with torch.enable_grad():
+        loss = optim.cross_entropy(logits, targets)
+        (g,) = torch.autograd.grad(loss * 65536.0, logits)
+        ref = torch.nn.functional.cross_entropy(logits, targets)
+        (rg,) = torch.autograd.grad(ref * 65536.0, logits)
+    assert abs(float(loss) - float(ref)) < 1e-6 and (g - rg).abs().max() < 1e-6 * 65536
+
+    shapes = [(768, 768), (768,), (3, 70000), (1, 1, 768), (21, 768)]
+    def make():
+        gen = torch.Generator().manual_seed(1)
+        return [torch.nn.Parameter(torch.randn(s, generator=gen).to(dev)) for s in shapes]
+    mine, theirs = make(), make()
+    a = optim.FusedAdam(mine, lr=1e-2, betas=(0.9, 0.999), eps=1e-7, weight_decay=0.01)
+    b = torch.optim.Adam(theirs, lr=1e-2, betas=(0.9, 0.999), eps=1e-7, weight_decay=0.01)
+    gen = torch.Generator().manual_seed(2)
+    for it in range(4):
+        grads = [torch.randn(s, generator=gen) * 0.1 for s in shapes]
+        for p, q, gr in zip(mine, theirs, grads):
+            p.grad, q.grad = gr.clone().to(dev), gr.clone().to(dev)
+        if it < 2:
+            a.step()
+            b.step()
+        else:                      # fused: gradients still carry the loss scale; clip to max_norm 1
+            scale = 1024.0
+            for p in mine:
+                p.grad.mul_(scale)
+            norm, found = a.step(grad_scale=scale, max_norm=1.0)
+            tn = torch.nn.utils.clip_grad_norm_(theirs, 1.0)
+            b.step()
+            assert float(found) == 0.0 and abs(float(norm) - float(tn)) < 1e-4 * float(tn)
+        for p, q in zip(mine, theirs):
+            assert (p - q).abs().max() < 2e-6, it
+    # a non-finite gradient skips the step and does not advance the step counter
+    before = [p.detach().clone() for p in mine]
+    for p in mine:
+        p.grad = torch.randn(p.shape, generator=gen).to(dev)
+    mine[2].grad[0, 5] = float('inf')
+    norm, found = a.step(grad_scale=1.0, max_norm=1.0)
+    assert float(found) == 1.0 and all(torch.equal(p, q) for p, q in zip(mine, before))
+    assert float(a._dev_state[0]['step']) == 4.0
