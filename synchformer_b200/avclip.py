@@ -9,6 +9,8 @@ three tiny torch ops (normalise, matmul, cross_entropy) - plumbing next to 52 TF
 In train mode (with autograd on) the towers take their differentiable path (train_encoders.py, SURVEY.md §8f N1: DropPath + hand-written
 backward), so `out['losses']['segment_contrastive_loss'].backward()` fills the gradients of both encoders and of `logit_scale`.
 """
+import logging
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -16,17 +18,59 @@ from torch import nn
 from .model import AST, MotionFormer
 
 
-class AVCLIP(nn.Module):
-    def __init__(self, n_embd: int = 768, init_scale: float = 0.07, clamp_scale_min: float = 0.001, clamp_scale_max: float = 0.5):
+class DoNothingBridge(nn.Identity):
+    """model.modules.bridges.DoNothingBridge (configs/segment_avclip.yaml:45-54): identity that accepts in_features / out_features."""
+
+    def __init__(self, in_features: int = None, out_features: int = None, **kwargs):
         super().__init__()
+
+
+def _tower_from_config(cfg, default_cls):
+    """`{target, params[, is_trainable]}` (segment_avclip.yaml:12-44) -> kernel-backed tower.  `ckpt_path` (pre-trained initialisation from
+    HF / a local .pyth) is harness work: it is dropped with a warning, load the weights with `load_state_dict`."""
+    if cfg is None:
+        return None
+    params = dict(cfg.get('params', {}) or {})
+    if params.pop('ckpt_path', None) is not None:
+        logging.warning('synchformer_b200.AVCLIP: ckpt_path is ignored - initialise the towers with load_state_dict')
+    name = str(cfg['target']).rsplit('.', 1)[-1]
+    if name != default_cls.__name__:
+        raise NotImplementedError(f"tower target {cfg['target']} is outside the B200 hot path (expected ...{default_cls.__name__})")
+    tower = default_cls(**params)
+    if cfg.get('is_trainable', True) is False:
+        tower.requires_grad_(False)
+    return tower
+
+
+class AVCLIP(nn.Module):
+    """Same constructor keywords as the reference class (open_clip/model.py:451-470), so `model.target=synchformer_b200.avclip.AVCLIP` is the
+    only change to configs/segment_avclip.yaml; with no tower configs it builds the segment_avclip.yaml towers."""
+
+    def __init__(self, n_embd: int = 768, afeat_extractor=None, vfeat_extractor=None, aproj=None, vproj=None, init_scale: float = 0.07,
+                 clamp_scale_min: float = 0.001, clamp_scale_max: float = 0.5, gather_for_loss: bool = False):
+        super().__init__()
+        if gather_for_loss:
+            raise NotImplementedError('gather_for_loss=True (global negatives across ranks) is not implemented; segment_avclip.yaml:11 uses False')
+        self.output_dict = True
         self.n_embd = n_embd
-        self.v_encoder = MotionFormer(extract_features=True, factorize_space_time=True, agg_space_module='TransformerEncoderLayer',
-                                      agg_time_module='AveragePooling', add_global_repr=False)
-        self.a_encoder = AST(extract_features=True, max_spec_t=66, factorize_freq_time=True, agg_freq_module='TransformerEncoderLayer',
-                             agg_time_module='AveragePooling', add_global_repr=False)
-        self.vproj, self.aproj = nn.Identity(), nn.Identity()            # model.modules.bridges.DoNothingBridge
-        self.clamp_scale_min, self.clamp_scale_max = clamp_scale_min, clamp_scale_max
+        self.v_encoder = _tower_from_config(vfeat_extractor, MotionFormer) or MotionFormer(
+            extract_features=True, factorize_space_time=True, agg_space_module='TransformerEncoderLayer', agg_time_module='AveragePooling',
+            add_global_repr=False)
+        self.a_encoder = _tower_from_config(afeat_extractor, AST) or AST(
+            extract_features=True, max_spec_t=66, factorize_freq_time=True, agg_freq_module='TransformerEncoderLayer',
+            agg_time_module='AveragePooling', add_global_repr=False)
+        for cfg in (aproj, vproj):
+            if cfg is not None and 'DoNothingBridge' not in str(cfg['target']):
+                raise NotImplementedError(f"bridge {cfg['target']}: only DoNothingBridge (segment_avclip.yaml:45-54) is implemented")
+        self.vproj, self.aproj = DoNothingBridge(), DoNothingBridge()
+        self.clamp_scale_min, self.clamp_scale_max, self.init_scale, self.gather_for_loss = clamp_scale_min, clamp_scale_max, init_scale, False
         self.logit_scale = nn.Parameter(torch.ones([]) * init_scale)
+
+    @torch.no_grad()
+    def clamp_logit_scales(self):
+        """open_clip/model.py:579-582: clamps the learned temperature in place (called at the top of every forward, :490)."""
+        self.logit_scale.clamp_(self.clamp_scale_min, self.clamp_scale_max)
+        return (self.logit_scale, None)
 
     def encode_streams(self, vis: torch.Tensor, aud: torch.Tensor, do_norm: bool = True):
         """open_clip/model.py:529-545: (B*S, 768) visual and audio segment features."""
@@ -43,11 +87,11 @@ class AVCLIP(nn.Module):
             return self._forward(vis, aud)
 
     def _forward(self, vis: torch.Tensor, aud: torch.Tensor):
-        scale = self.logit_scale.clamp(self.clamp_scale_min, self.clamp_scale_max)
+        logit_scales = self.clamp_logit_scales()
         vfeat, afeat = self.encode_streams(vis, aud)
         sim_v2a = vfeat @ afeat.mT / self.logit_scale                     # compute_loss :507-513
         sim_a2v = afeat @ vfeat.mT / self.logit_scale
         tgt = torch.eye(*sim_v2a.shape, device=sim_v2a.device, dtype=sim_v2a.dtype)
         loss = (F.cross_entropy(sim_v2a, tgt) + F.cross_entropy(sim_a2v, tgt)) / 2
-        return {'rgb_features': (vfeat, None), 'audio_features': (afeat, None), 'logit_scales': scale,
+        return {'rgb_features': (vfeat, None), 'audio_features': (afeat, None), 'logit_scales': logit_scales,
                 'losses': {'segment_contrastive_loss': loss}}
