@@ -338,17 +338,6 @@ class AST(_KernelModule):
         return feats.mean(dim=2) if self.time_pool else feats
 
 
-class _NoDropout:
-    """View of a GlobalTransformer with every dropout probability forced to 0 (gradients in eval mode)."""
-    tok_pdrop = embd_pdrop = resid_pdrop = attn_pdrop = 0.0
-
-    def __init__(self, tr):
-        self._tr = tr
-
-    def __getattr__(self, name):
-        return getattr(self._tr, name)
-
-
 class GlobalTransformer(_KernelModule):
     """Synchronisation transformer (sync_model.py:117-173): 3 pre-norm blocks, 8 heads x 96, LN eps 1e-5, erf GELU.
     `pos_emb_cfg.pos_emb` is the RandInitPositionalEncoding table (modules/transformer.py:120-130)."""
@@ -391,12 +380,11 @@ class GlobalTransformer(_KernelModule):
     def forward(self, v: torch.Tensor, a: torch.Tensor, targets=None, attempt_to_apply_heads=True):
         """v (B, 8S, 768), a (B, 6S, 768) projected features -> logits (B, n_cls).  sync_model.py:150-173 (eval: dropouts are identity)."""
         ops.require_cuda(v, 'v')
-        if self.training or (torch.is_grad_enabled() and (v.requires_grad or a.requires_grad or any(p.requires_grad for p in self.parameters()))):
-            # SURVEY.md §8f N3: dropout + autograd-visible forward / hand-written backward (train.py); eval + no_grad takes the path below
+        if self.training:
+            # SURVEY.md §8f N3: dropout + autograd-visible forward / hand-written backward (train.py).  eval() always takes the inference
+            # path below (no autograd graph), whatever torch.is_grad_enabled() says.
             if not attempt_to_apply_heads and self._HEAD == 'off_head':
                 raise NotImplementedError('training without the classification head is not implemented')
-            if not self.training:                                                   # eval-mode gradients: same kernels, dropout off
-                return train.sync_transformer(_NoDropout(self), v, a)
             return train.sync_transformer(self, v, a)
         B, Sv, _ = v.shape
         Sa = a.shape[1]
@@ -491,8 +479,7 @@ class Synchformer(nn.Module):
         """vproj / aproj (sync_model.py:55-56) + segment flattening (:59-62).  (B,S,8,768),(B,S,6,768) -> (B,8S,768),(B,6S,768) fp32."""
         B, S = vis.shape[:2]
         Wp = self._proj_weights()
-        if self.training or (torch.is_grad_enabled() and (vis.requires_grad or aud.requires_grad or self.vproj.weight.requires_grad
-                                                          or self.aproj.weight.requires_grad)):
+        if self.training:
             v = train.linear(vis.float().contiguous().view(-1, D), self.vproj.weight, self.vproj.bias, Wp['v'])        # N3: differentiable
             a = train.linear(aud.float().contiguous().view(-1, D), self.aproj.weight, self.aproj.bias, Wp['a'])
             return v.view(B, S * 8, D), a.view(B, S * 6, D)
