@@ -465,3 +465,13 @@ def encoders_train_grads(sd, vis: Tensor, aud: Tensor, drop_path: Optional[dict]
         loss = contrastive_loss(v, a, logit_scale)
         grads = torch.autograd.grad(loss, [leaves[k] for k in names])
     return loss.detach(), v.detach(), a.detach(), dict(zip(names, grads))
+
+
+def shift_and_get_preds(a: Tensor, v: Tensor, W: int):
+    """training/train.py:549-579 restated: sliding windows of W segments over (B, S, D) features, all-pairs window similarity, top-1 in
+    both directions -> (preds_a, preds_v) each (B, S - W + 1); also returns the similarity matrix for tolerance-aware comparisons."""
+    B, S, D_ = a.shape
+    af = a.unfold(-2, W, 1).contiguous().view(B, S - W + 1, D_ * W)
+    vf = v.unfold(-2, W, 1).contiguous().view(B, S - W + 1, D_ * W)
+    sim = af @ vf.mT
+    return torch.argmax(sim, dim=-2), torch.argmax(sim, dim=-1), sim

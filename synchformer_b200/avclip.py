@@ -95,3 +95,30 @@ class AVCLIP(nn.Module):
         loss = (F.cross_entropy(sim_v2a, tgt) + F.cross_entropy(sim_a2v, tgt)) / 2
         return {'rgb_features': (vfeat, None), 'audio_features': (afeat, None), 'logit_scales': logit_scales,
                 'losses': {'segment_contrastive_loss': loss}}
+
+
+def shift_and_get_preds(a: torch.Tensor, v: torch.Tensor, W: int):
+    """Zero-shot shifted-window evaluation of the stage-I features (training/train.py:549-579): for every window of W
+    consecutive segments of the audio track, the most similar window of the visual track and vice versa.
+    a, v (B, S, D) segment features -> (preds_a, preds_v), each (B, S - W + 1) int64.
+
+    sim[b, i, j] = <a[b, i:i+W], v[b, j:j+W]> = sum_w seg[b, i + w, j + w] with seg[b] = a[b] v[b]^T: the segment-by-segment products of the
+    whole batch are ONE tensor-core GEMM ((B S, D) x (B S, D)^T, fp32 out; the cross-clip blocks are discarded), the window sums and the
+    arg-max are index plumbing on the (B, S, S) result."""
+    from . import ops
+    assert a.shape == v.shape and a.dim() == 3, f'{tuple(a.shape)} != {tuple(v.shape)}'
+    B, S, D = a.shape
+    n_shifts = S - W + 1
+    assert n_shifts >= 1, f'window {W} longer than the {S} segments'
+    ops.require_cuda(a, 'a')
+    ab = ops.cast_bf16(a.float().contiguous().view(B * S, D))
+    vb = ops.cast_bf16(v.float().contiguous().view(B * S, D))
+    pad = (-(B * S)) % 8                                         # the GEMM wants N % 8 == 0: pad the visual rows with zeros
+    if pad:
+        vb = torch.cat([vb, vb.new_zeros((pad, D))], dim=0)
+    full = ops.gemm(ab, vb, None, out_f32=True)[:, :B * S].reshape(B, S, B, S)
+    idx = torch.arange(B, device=a.device)
+    seg = full[idx, :, idx, :]                                   # (B, S, S): a[b, i] . v[b, j]
+    win = seg.unfold(1, W, 1).unfold(2, W, 1)                    # (B, n, n, W, W)
+    sim = win.diagonal(dim1=-2, dim2=-1).sum(-1)                 # (B, n, n)
+    return torch.argmax(sim, dim=-2), torch.argmax(sim, dim=-1)

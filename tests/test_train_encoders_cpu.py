@@ -169,3 +169,16 @@ def test_avclip_train_mode_routes_through_the_differentiable_towers(monkeypatch)
     with pytest.raises(Exception):            # eval keeps the inference kernels, which need the GPU library: never the differentiable path
         model(torch.zeros(1, 2, 3, 16, 224, 224), torch.zeros(1, 2, 66, 128))
     assert calls == []
+
+
+@pytest.mark.parametrize('B,S,W', [(3, 14, 8), (2, 5, 5), (1, 7, 1)])
+def test_shifted_window_eval_host_logic(monkeypatch, B, S, W):
+    """avclip.shift_and_get_preds (one GEMM + index plumbing) == the reference's unfold + bmm formulation (training/train.py:549-579)."""
+    from synchformer_b200 import avclip
+    fake_ops.install(monkeypatch, round_bf16=False, names=('require_cuda', 'cast_bf16', 'gemm'))
+    torch.manual_seed(S)
+    a, v = torch.randn(B, S, 768), torch.randn(B, S, 768)
+    v = v + 0.5 * a.roll(1, dims=1)                              # some structure so that the arg-max is not a coin flip
+    pa, pv = avclip.shift_and_get_preds(a, v, W)
+    ra, rv, _ = O.shift_and_get_preds(a, v, W)
+    assert pa.shape == (B, S - W + 1) and torch.equal(pa, ra) and torch.equal(pv, rv)

@@ -155,3 +155,20 @@ def test_stage_two_with_trainable_extractors(cuda_device):
     want = {n for n, p in model.named_parameters() if '.patch_embed.proj.' not in n}
     assert got == want, (want - got, got - want)
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_shifted_window_eval(cuda_device):
+    """N4: avclip.shift_and_get_preds on the GPU GEMM against the reference formulation; ties are avoided by construction, and the
+    predictions must agree wherever the fp32 similarity margin exceeds the bf16 operand noise."""
+    torch.manual_seed(0)
+    B, S, W = 16, 14, 8
+    a = torch.nn.functional.normalize(torch.randn(B, S, 768), dim=-1)
+    v = torch.nn.functional.normalize(a + 0.3 * torch.randn(B, S, 768), dim=-1)          # in-sync tracks: the diagonal wins clearly
+    pa, pv = avclip.shift_and_get_preds(a.to(cuda_device), v.to(cuda_device), W)
+    ra, rv, sim = O.shift_and_get_preds(a, v, W)
+    top2 = sim.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 0.05
+    assert clear.float().mean() > 0.9
+    assert torch.equal(pv.cpu()[clear], rv[clear])
+    gt = torch.arange(S - W + 1).view(1, -1)
+    assert (pv.cpu() == gt).float().mean() > 0.9 and (pa.cpu() == gt).float().mean() > 0.9
