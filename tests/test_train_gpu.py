@@ -279,13 +279,13 @@ def test_full_forward_in_train_mode_with_frozen_extractors_and_optimizer_steps(c
     sd = synth.synthetic_state_dict(1337, n_segments=S)
     model = _train_model(S, 0.1, sd, cuda_device)
     vis = synth.synthetic_video(2, S, 0).to(cuda_device).half()
-    with torch.no_grad():
-        aud = ops.mel_frontend(synth.synthetic_waveform(2, S, 0).to(cuda_device)).unsqueeze(2)
+    aud = O.mel_frontend(synth.synthetic_waveform(2, S, 0)).float().unsqueeze(2).to(cuda_device)
     targets = torch.tensor([3, 17], device=cuda_device)
     opt = torch.optim.Adam(model.parameters(), 2e-4, (0.9, 0.999), 1e-7, 0.0)
-    scaler = torch.amp.GradScaler('cuda', enabled=True)
-    frozen_before = model.vfeat_extractor.blocks[3].attn.qkv.weight.detach().clone()
-    moved_before = model.transformer.blocks[1].attn.query.weight.detach().clone()
+    scaler = torch.amp.GradScaler(cuda_device.type, enabled=cuda_device.type == 'cuda')
+    params = dict(model.named_parameters())
+    frozen, moved = params['vfeat_extractor.blocks.3.attn.qkv.weight'], params['transformer.blocks.1.attn.query.weight']
+    frozen_before, moved_before = frozen.detach().clone(), moved.detach().clone()
     losses = []
     for _ in range(6):
         opt.zero_grad(set_to_none=True)
@@ -298,8 +298,8 @@ def test_full_forward_in_train_mode_with_frozen_extractors_and_optimizer_steps(c
         assert torch.isfinite(loss)
         losses.append(float(loss))
     assert all(p.grad is None for p in model.vfeat_extractor.parameters()) and all(p.grad is None for p in model.afeat_extractor.parameters())
-    assert torch.equal(frozen_before, model.vfeat_extractor.blocks[3].attn.qkv.weight.detach())
-    assert not torch.equal(moved_before, model.transformer.blocks[1].attn.query.weight.detach())
+    assert torch.equal(frozen_before, frozen.detach())
+    assert not torch.equal(moved_before, moved.detach())
     assert min(losses[3:]) < losses[0], losses
     model.eval()                                                        # and the eval path still works on the updated weights
     with torch.no_grad():
