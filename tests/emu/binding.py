@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  `install(monkeypatch)` makes the REAL wrappers of ops.py (dropout, gelu_fwd / gelu_bwd, transpose_bf16,
 colsum, layernorm_bwd, attention_train_fwd / _bwd, sync_head_bwd) call the REAL C-ABI entry points and the REAL kernel code, compiled
-for the emulator, on CPU tensors; the kernels that were verified on hardware in round 1 and are not part of N3 (gemm, layernorm,
-sync_tokens, sync_head, cast) are served by the torch stand-ins of tests/fake_ops.py with real bf16 dtypes.
+for the emulator, on CPU tensors.  The PTX-free kernels that were verified on hardware in round 1 (LayerNorm, token assembly, im2col, casts,
+head) are emulated from their real sources too - which checks the emulator against kernels known to be right; only the tcgen05 / mma.sync
+kernels (GEMM, attention forward) are served by the torch stand-ins of tests/fake_ops.py with real bf16 dtypes.
 """
 import ctypes
 import os
@@ -15,9 +16,11 @@ sys.path.insert(0, os.path.dirname(HERE))
 EMULATED = ('sfb_dropout', 'sfb_gelu_fwd', 'sfb_gelu_bwd', 'sfb_transpose_bf16', 'sfb_colsum', 'sfb_layernorm_bwd_workspace_floats',
             'sfb_layernorm_bwd', 'sfb_attention_train_fwd', 'sfb_attention_train_bwd', 'sfb_sync_head_bwd', 'sfb_last_error',
             'sfb_attention_bwd_stats_floats', 'sfb_attention_bwd', 'sfb_attention_bwd_global_query', 'sfb_droppath', 'sfb_gather_rows_bf16',
-            'sfb_cross_entropy', 'sfb_optim_chunk_elems', 'sfb_grad_sqnorm', 'sfb_adam_step')
-STAND_INS = ('require_cuda', 'cast_bf16', 'gemm', 'layernorm', 'sync_tokens', 'sync_head', 'im2col_video', 'video_tokens', 'im2col_ast',
-             'ast_tokens', 'attention')
+            'sfb_cross_entropy', 'sfb_optim_chunk_elems', 'sfb_grad_sqnorm', 'sfb_adam_step',
+            # verified on the B200 in round 1 (no inline PTX): emulating them checks the emulator against kernels known to be right
+            'sfb_layernorm', 'sfb_im2col_video', 'sfb_im2col_video_clip', 'sfb_video_tokens', 'sfb_im2col_ast', 'sfb_ast_tokens', 'sfb_sync_tokens',
+            'sfb_sync_head', 'sfb_cast_f32_bf16')
+STAND_INS = ('require_cuda', 'gemm', 'attention')          # tcgen05 / mma.sync kernels: not emulated, torch stand-ins (hardware-verified in round 1)
 
 _emu = None
 

@@ -16,7 +16,9 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(REPO, 'synchformer_b200', 'csrc')
 OUT = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT, 'libsfb_emu.so')
-SOURCES = ['train.cu', 'attention_train.cu', 'attention_bwd.cu', 'optim.cu']
+SOURCES = ['train.cu', 'attention_train.cu', 'attention_bwd.cu', 'optim.cu',
+           # kernels that were verified on the B200 in round 1 and contain no inline PTX: running them here validates the emulator itself
+           'layernorm.cu', 'embed.cu']
 CUDA_INC = os.environ.get('CUDA_INC', '/usr/local/cuda/include')
 
 
@@ -56,7 +58,14 @@ def rewrite_launches(text: str) -> str:
         if k < 0:
             return out + text[pos:]
         name_start = k
-        while name_start > 0 and re.match(r'[A-Za-z0-9_:<>]', text[name_start - 1]):
+        if text[name_start - 1] == '>':                       # template arguments (may contain spaces): back to the matching '<'
+            depth = 0
+            while True:
+                name_start -= 1
+                depth += {'>': 1, '<': -1}.get(text[name_start], 0)
+                if depth == 0:
+                    break
+        while name_start > 0 and re.match(r'[A-Za-z0-9_:]', text[name_start - 1]):
             name_start -= 1
         cfg_end = text.index('>>>', k)
         cfg = _split_top(text[k + 3:cfg_end])

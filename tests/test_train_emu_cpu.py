@@ -9,6 +9,7 @@ import os
 import pytest
 import torch
 
+import fake_ops
 import test_train_gpu as G
 from emu import binding
 
@@ -104,3 +105,43 @@ def test_no_out_of_bounds_access_under_guard_pages():
 
 
 test_fused_cross_entropy_and_adam = G.test_fused_cross_entropy_and_adam
+
+
+def test_emulator_reproduces_kernels_that_are_verified_on_hardware(monkeypatch):
+    """Credibility check of the emulator itself: LayerNorm (plain, gathered, fused double), token assembly, im2col, cast and the head kernel
+    passed their parity tests on the B200 in round 1 (tests/test_kernels_gpu.py); the same sources run here must reproduce their contracts."""
+    binding.install(monkeypatch)
+    from synchformer_b200 import ops
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    D = 768
+    x = torch.randn(3 * 74, D) * 2 + 0.3
+    g1, b1, g2, b2 = torch.rand(D) + 0.5, torch.randn(D) * 0.1, torch.rand(D) + 0.5, torch.randn(D) * 0.1
+    ref = F.layer_norm(x, (D,), g1, b1, 1e-6)
+    assert (ops.layernorm(x, g1, b1, 1e-6, out_f32=True) - ref).abs().max() < 2e-5
+    assert torch.equal(ops.layernorm(x, g1, b1, 1e-6), fake_ops.layernorm(x, g1, b1, 1e-6).to(torch.bfloat16)) or \
+        (ops.layernorm(x, g1, b1, 1e-6).float() - ref).abs().max() < 2e-2
+    rows = 3 * 72
+    got = ops.layernorm(x, g1, b1, 1e-12, rows=rows, group=72, group_stride=74, offset=2, gamma2=g2, beta2=b2, eps2=1e-6, out_f32=True)
+    sel = x.view(3, 74, D)[:, 2:].reshape(rows, D)
+    assert (got - F.layer_norm(F.layer_norm(sel, (D,), g1, b1, 1e-12), (D,), g2, b2, 1e-6)).abs().max() < 5e-5
+    # token assembly of the three streams + casts + head
+    B, S = 2, 3
+    v, a = torch.randn(B * 8 * S, D), torch.randn(B * 6 * S, D)
+    off, mod, pos = torch.randn(1, 1, D), torch.randn(1, 1, D), torch.randn(1, 2 + 14 * S, D)
+    assert (ops.sync_tokens(v, a, g1, b1, g2, b2, 1e-5, off, mod, pos, B, S) - fake_ops.sync_tokens(v, a, g1, b1, g2, b2, 1e-5, off, mod, pos, B, S)).abs().max() < 5e-5
+    xs = torch.randn(B * (2 + 14 * S), D)
+    W, bias = torch.randn(21, D) * 0.03, torch.randn(21)
+    assert (ops.sync_head(xs, 2 + 14 * S, g1, b1, 1e-5, W, bias, B) - fake_ops.sync_head(xs, 2 + 14 * S, g1, b1, 1e-5, W, bias, B)).abs().max() < 1e-4
+    assert torch.equal(ops.cast_bf16(x), x.to(torch.bfloat16))
+    spec = torch.randn(2, 128, 66)
+    assert torch.equal(ops.im2col_ast(spec), spec.unfold(1, 16, 10).unfold(2, 16, 10).reshape(2 * 72, 256).to(torch.bfloat16))
+    patch = torch.randn(2 * 72, D)
+    cls, dist, apos = torch.randn(1, 1, D), torch.randn(1, 1, D), torch.randn(1, 74, D)
+    assert torch.equal(ops.ast_tokens(patch, cls, dist, apos, 2), fake_ops.ast_tokens(patch, cls, dist, apos, 2))
+    vpatch, vcls, vpos, vtmp = torch.randn(1568, D), torch.randn(1, 1, D), torch.randn(1, 197, D), torch.randn(1, 8, D)
+    assert (ops.video_tokens(vpatch, vcls, vpos, vtmp, 1) - fake_ops.video_tokens(vpatch, vcls, vpos, vtmp, 1)).abs().max() < 1e-6
+    vis = torch.randint(0, 256, (1, 16, 3, 224, 224), dtype=torch.uint8)
+    want = fake_ops.im2col_video((vis.float() / 255.0 - 0.5) / 0.5)
+    assert (ops.im2col_video(vis).float() - want.float()).abs().max() < 1e-2                       # uint8 path: normalisation fused into the gather
+    assert torch.equal(ops.im2col_video(vis.float()), fake_ops.im2col_video(vis.float()))
