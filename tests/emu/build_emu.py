@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT, 'libsfb_emu.so')
 SOURCES = ['train.cu', 'attention_train.cu', 'attention_bwd.cu', 'optim.cu',
            # kernels that were verified on the B200 in round 1 and contain no inline PTX: running them here validates the emulator itself
-           'layernorm.cu', 'embed.cu']
+           'layernorm.cu', 'embed.cu', 'attention.cu']
 CUDA_INC = os.environ.get('CUDA_INC', '/usr/local/cuda/include')
 
 
@@ -80,15 +80,64 @@ def rewrite_launches(text: str) -> str:
     return out
 
 
+PTX = [  # (substring of the PTX text, emulator function, uses outputs)
+    ('cp.async.cg.shared.global', 'emu::ptx_cp_async16'), ('cp.async.commit_group', 'emu::ptx_nop'), ('cp.async.wait_group', 'emu::ptx_nop'),
+    ('ldmatrix.sync.aligned.m8n8.x4.trans', 'emu::ptx_ldmatrix_x4_trans'), ('ldmatrix.sync.aligned.m8n8.x4', 'emu::ptx_ldmatrix_x4'),
+    ('ldmatrix.sync.aligned.m8n8.x2', 'emu::ptx_ldmatrix_x2'), ('mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32', 'emu::ptx_mma_16816'),
+    ('ex2.approx.ftz.f32', 'emu::ptx_ex2'),
+]
+
+
+def rewrite_asm(text: str) -> str:
+    """`asm [volatile]("ptx" : outs : ins : clobbers);` -> `emu::ptx_xxx(out expressions..., in expressions...);` for the instructions in PTX."""
+    out, pos = '', 0
+    for m in re.finditer(r'\basm\s*(?:volatile\s*)?\(', text):
+        if m.start() < pos:
+            continue
+        end = _match(text, m.end() - 1, '(', ')')
+        body = text[m.end():end - 1]
+        strings = re.findall(r'"((?:[^"\\]|\\.)*)"', body.split(':')[0] if ':' in body else body)
+        ptx = ''.join(strings)
+        sections, depth, cur, in_str = [], 0, '', False
+        for ch in body:
+            if ch == '"':
+                in_str = not in_str
+            if not in_str:
+                depth += {'(': 1, ')': -1}.get(ch, 0)
+                if ch == ':' and depth == 0:
+                    sections.append(cur)
+                    cur = ''
+                    continue
+            cur += ch
+        sections.append(cur)
+        operands = []
+        for sec in sections[1:3]:
+            for op in _split_top(sec):
+                mm = re.match(r'\s*"[^"]*"\s*\((.*)\)\s*$', op, re.S)
+                if mm:
+                    operands.append(mm.group(1).strip())
+        fn = next((f for key, f in PTX if key in ptx), None)
+        if fn is None:
+            raise ValueError(f'no emulation for PTX: {ptx[:80]}')
+        if fn == 'emu::ptx_nop':
+            operands = []
+        out += text[pos:m.start()] + f'{fn}({", ".join(operands)})'
+        pos = end
+    return out + text[pos:]
+
+
 def transform(text: str) -> str:
-    text = re.sub(r'extern\s+__shared__\s+__align__\(\d+\)\s+unsigned char (\w+)\[\];', r'unsigned char *\1 = emu::dyn_smem();', text)
+    if 'asm' in text:
+        text = rewrite_asm(text)
+    text = re.sub(r'extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?((?:unsigned char)|\w+)\s+(\w+)\[\];',
+                  r'\1 *\2 = reinterpret_cast<\1 *>(emu::dyn_smem());', text)
     return rewrite_launches(text)
 
 
 def build(force: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
     h = hashlib.sha256()
-    for f in SOURCES + ['philox.cuh']:
+    for f in SOURCES + ['philox.cuh', 'attention.cuh']:
         h.update(open(os.path.join(CSRC, f), 'rb').read())
     for f in ('common.cuh', 'build_emu.py'):
         h.update(open(os.path.join(HERE, f), 'rb').read())
@@ -103,10 +152,15 @@ def build(force: bool = False) -> str:
         gen.append(dst)
     with open(os.path.join(OUT, 'common.cuh'), 'w') as fh:          # quote-includes look next to the including file first
         fh.write('#include "../common.cuh"\n')
+    with open(os.path.join(OUT, 'attention.cuh'), 'w') as fh:       # same header without <cuda_runtime.h> (the shim provides the types)
+        fh.write(open(os.path.join(CSRC, 'attention.cuh')).read().replace('#include <cuda_runtime.h>', ''))
     extra = os.path.join(OUT, 'emu_exports.cpp')
     with open(extra, 'w') as fh:
         fh.write('#define EMU_MAIN_TU 1\n#include "common.cuh"\nextern "C" const char *sfb_last_error(void) { return sfb::err_buf(); }\n'
                  'extern "C" long emu_launch_count(void) { return emu::S().launches; }\n'
+                 '#include "attention.cuh"\n'        # the tcgen05 space-attention kernel is not emulated: report it as unsupported
+                 'namespace sfb { namespace attn { bool tc_supported(const Desc &) { return false; } '
+                 'int launch_tc(const Desc &, cudaStream_t) { return SFB_E_UNSUPPORTED; } } }\n'
                  'extern "C" void emu_set_schedule(int mode, unsigned long long seed) { emu::schedule() = mode; emu::rng() = seed * 2 + 1; }\n')
     cmd = ['g++', '-O2', '-g', '-std=c++17', '-shared', '-fPIC', '-w', '-I', OUT, '-I', CSRC, '-I', CUDA_INC, '-o', LIB] + gen + [extra]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -46,6 +46,9 @@ inline cudaError_t emu_cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) {
     memset(p, v, n);
     return cudaSuccess;
 }
+template <typename K>
+inline cudaError_t emu_cudaOccupancy(int *n, K, int, size_t) { *n = 1; return cudaSuccess; }
+#define cudaOccupancyMaxActiveBlocksPerMultiprocessor emu_cudaOccupancy
 #define cudaGetErrorString emu_cudaGetErrorString
 #define cudaGetLastError emu_cudaGetLastError
 #define cudaFuncSetAttribute emu_cudaFuncSetAttribute
@@ -107,6 +110,7 @@ inline uint64_t &rng() { static uint64_t r = 0x9E3779B97F4A7C15ull; return r; }
 struct Sched {
     std::vector<Thread> threads;
     std::vector<uint64_t> slot;       // per-thread exchange slot for shuffles
+    std::vector<uint32_t> wide;       // per-thread 8-word exchange area for ldmatrix / mma fragments
 #if EMU_FAST_SWITCH
     void *main_sp = nullptr;
 #else
@@ -271,7 +275,97 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     return r;
 }
 template <typename T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    emu::Sched &s = emu::S();
+    const int me = s.cur;
+    uint64_t bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    s.slot[me] = bits;
+    __syncwarp();
+    uint64_t got = s.slot[(me & ~31) | (src_lane & 31)];
+    __syncwarp();
+    T r;
+    memcpy(&r, &got, sizeof(T));
+    return r;
+}
+template <typename T>
 inline T __ldg(const T *p) { return *p; }
+
+// ---- the few PTX instructions the hardware-verified mma.sync attention kernels use (build_emu.py rewrites their asm statements into
+// these calls).  Shared-memory "addresses" are byte offsets into the dynamic shared memory of the running block. -------------------------
+inline size_t __cvta_generic_to_shared(const void *p) { return static_cast<size_t>(reinterpret_cast<const unsigned char *>(p) - emu::dyn_smem()); }
+namespace emu {
+inline void warp_publish(const uint32_t *mine, int n) {          // every lane stores n words; visible to the warp after the rendezvous
+    Sched &s = S();
+    if (s.wide.size() < s.threads.size() * 8) s.wide.resize(s.threads.size() * 8);
+    for (int k = 0; k < n; ++k) s.wide[static_cast<size_t>(s.cur) * 8 + k] = mine[k];
+    __syncwarp();
+}
+inline uint32_t warp_peek(int lane, int k) { return S().wide[static_cast<size_t>((S().cur & ~31) | lane) * 8 + k]; }
+inline void ptx_cp_async16(uint32_t dst, const void *src) { memcpy(dyn_smem() + dst, src, 16); }
+inline void ptx_nop() {}
+// ldmatrix .m8n8 .b16: lane 8 i + r supplies the address of row r of matrix i; lane T receives, per matrix, the 32-bit word holding
+// elements (T / 4, 2 (T % 4)) and (T / 4, 2 (T % 4) + 1) - or, with .trans, elements (2 (T % 4), T / 4) and (2 (T % 4) + 1, T / 4)
+inline void ldmatrix(bool trans, int n_mat, uint32_t addr, uint32_t *out) {
+    warp_publish(&addr, 1);
+    const int T = S().cur & 31;
+    for (int i = 0; i < n_mat; ++i) {
+        if (!trans) {
+            const unsigned char *row = dyn_smem() + warp_peek(8 * i + T / 4, 0);
+            memcpy(&out[i], row + 4 * (T % 4), 4);
+        } else {
+            uint16_t lo, hi;
+            memcpy(&lo, dyn_smem() + warp_peek(8 * i + 2 * (T % 4), 0) + 2 * (T / 4), 2);
+            memcpy(&hi, dyn_smem() + warp_peek(8 * i + 2 * (T % 4) + 1, 0) + 2 * (T / 4), 2);
+            out[i] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+        }
+    }
+    __syncwarp();
+}
+inline void ptx_ldmatrix_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr) {
+    uint32_t o[4];
+    ldmatrix(false, 4, addr, o);
+    r0 = o[0], r1 = o[1], r2 = o[2], r3 = o[3];
+}
+inline void ptx_ldmatrix_x4_trans(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr) {
+    uint32_t o[4];
+    ldmatrix(true, 4, addr, o);
+    r0 = o[0], r1 = o[1], r2 = o[2], r3 = o[3];
+}
+inline void ptx_ldmatrix_x2(uint32_t &r0, uint32_t &r1, uint32_t addr) {
+    uint32_t o[2];
+    ldmatrix(false, 2, addr, o);
+    r0 = o[0], r1 = o[1];
+}
+inline float bf16_half(uint32_t w, int hi) {
+    const uint32_t bits = hi ? (w & 0xffff0000u) : (w << 16);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+// mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 (PTX ISA fragment layouts; g = lane / 4, t = lane % 4):
+//   A: a0 (g, 2t..), a1 (g + 8, 2t..), a2 (g, 2t + 8..), a3 (g + 8, 2t + 8..);  B: b0 (k = 2t.., n = g), b1 (k = 2t + 8.., n = g)
+//   C / D: c0 (g, 2t), c1 (g, 2t + 1), c2 (g + 8, 2t), c3 (g + 8, 2t + 1)
+inline void ptx_mma_16816(float &c0, float &c1, float &c2, float &c3, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    const uint32_t mine[6] = {a0, a1, a2, a3, b0, b1};
+    warp_publish(mine, 6);
+    const int T = S().cur & 31, g = T / 4, t = T % 4;
+    float *c[4] = {&c0, &c1, &c2, &c3};
+    for (int q = 0; q < 4; ++q) {
+        const int row = g + 8 * (q / 2), col = 2 * t + (q % 2);
+        float acc = *c[q];
+        for (int k = 0; k < 16; ++k) {
+            const int a_lane = (row % 8) * 4 + (k % 8) / 2, a_reg = (row / 8) + 2 * (k / 8);
+            const int b_lane = col * 4 + (k % 8) / 2, b_reg = 4 + k / 8;
+            acc += bf16_half(warp_peek(a_lane, a_reg), k % 2) * bf16_half(warp_peek(b_lane, b_reg), k % 2);
+        }
+        *c[q] = acc;
+    }
+    __syncwarp();
+}
+inline void ptx_ex2(float &y, float x) { y = exp2f(x); }
+}  // namespace emu
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32); }
 inline float __uint_as_float(uint32_t u) {
     float f;
@@ -279,6 +373,8 @@ inline float __uint_as_float(uint32_t u) {
     return f;
 }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline float __expf(float x) { return expf(x); }
+inline float __fdividef(float a, float b) { return a / b; }
 using std::max;
 using std::min;
 

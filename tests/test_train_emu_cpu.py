@@ -145,3 +145,43 @@ def test_emulator_reproduces_kernels_that_are_verified_on_hardware(monkeypatch):
     want = fake_ops.im2col_video((vis.float() / 255.0 - 0.5) / 0.5)
     assert (ops.im2col_video(vis).float() - want.float()).abs().max() < 1e-2                       # uint8 path: normalisation fused into the gather
     assert torch.equal(ops.im2col_video(vis.float()), fake_ops.im2col_video(vis.float()))
+
+
+def test_emulated_mma_attention_kernels_match_the_dense_definition(monkeypatch):
+    """The mma.sync / ldmatrix / cp.async attention kernels of csrc/attention.cu (parity-green on the B200 in round 1) run here with their PTX
+    emulated instruction by instruction (fragment layouts of the PTX ISA, tests/emu/common.cuh).  That they reproduce the dense softmax
+    attention validates the emulator's warp-level semantics against kernels known to be right on hardware - and keeps the forward attention
+    of the emulated training tests on real kernel code (only the tcgen05 variants are replaced: the GEMM by a torch stand-in, the
+    196 x 197 tcgen05 kernel by the mma kernel it superseded)."""
+    import math
+    binding.install(monkeypatch)
+    from synchformer_b200 import ops
+    torch.manual_seed(0)
+    D = 768
+    row = 3 * D
+
+    def run(rows, kw, q_off=0, prefix=None, impl=None):
+        qkv = (torch.randn(rows, 3 * D) * 0.8).to(torch.bfloat16)
+        got, want = torch.zeros(rows, D, dtype=torch.bfloat16), torch.zeros(rows, D, dtype=torch.bfloat16)
+        q, k, v = qkv[q_off:], qkv[q_off:, D:], qkv[q_off:, 2 * D:]
+        pk = dict(k_prefix=qkv[:, D:], v_prefix=qkv[:, 2 * D:], prefix_outer=prefix) if prefix is not None else {}
+        ops.attention(q, k, v, got[q_off:], impl=impl, **kw, **pk)
+        monkeypatch.setattr(fake_ops, 'REAL_DTYPES', True)
+        fake_ops.attention(q, k, v, want[q_off:], **kw, **pk)
+        return float((got.float() - want.float()).abs().max())
+
+    n, T = 2, 74
+    assert run(n * T, dict(q_strides=(T * row, 0, row), kv_strides=(T * row, 0, row), o_strides=(T * D, 0, D), n_outer=n, n_inner=1, n_heads=12,
+                           head_dim=64, Lq=T, Lk=T, scale=0.125)) < 8e-3                                      # AST: attn_mma_kernel<64>
+    T = 30
+    kw = dict(q_strides=(T * row, 0, row), kv_strides=(T * row, 0, row), o_strides=(T * D, 0, D), n_outer=n, n_inner=1, n_heads=8, head_dim=96, Lq=T,
+              Lk=T, scale=1 / math.sqrt(96))
+    assert run(n * T, kw) < 1.6e-2 and run(n * T, kw, impl=1) < 8e-3                                          # sync: attn_mma_kernel<96>, generic
+    TOK, n = 1569, 1
+    seg = TOK * row
+    assert run(n * TOK, dict(q_strides=(seg, row, 196 * row), kv_strides=(seg, row, 196 * row), o_strides=(TOK * D, D, 196 * D), n_outer=n, n_inner=196,
+                             n_heads=12, head_dim=64, Lq=8, Lk=8, scale=0.125), q_off=1, prefix=seg) < 1.6e-2       # attn_time_mma_kernel
+    assert run(n * TOK, dict(q_strides=(seg, 0, row), kv_strides=(seg, 0, row), o_strides=(TOK * D, 0, D), n_outer=n, n_inner=1, n_heads=12, head_dim=64,
+                             Lq=1, Lk=TOK, scale=0.125)) < 8e-3                                                # attn_row1_kernel
+    assert run(n * TOK, dict(q_strides=(seg, 196 * row, row), kv_strides=(seg, 196 * row, row), o_strides=(TOK * D, 196 * D, D), n_outer=n, n_inner=8,
+                             n_heads=12, head_dim=64, Lq=196, Lk=196, scale=0.125), q_off=1, prefix=seg) < 8e-3     # space: attn_mma_kernel<64>
