@@ -13,6 +13,8 @@
 // row, Q / dO staged) writes dK / dV.  The prefix key is shared by all inner problems of an outer index, so its dK / dV go to a
 // per-problem fp32 buffer that the caller reduces (sfb_colsum) - no atomics, deterministic.  fp32 math on the CUDA cores: these
 // problems are 3 % of the encoder FLOPs in the forward; a tensor-core version is a later optimisation, correctness comes first.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -208,6 +210,267 @@ __global__ void __launch_bounds__(kWarps * 32) attn_bwd_dkv_kernel(const Desc d)
             }
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant for the large problems (head_dim 64, 64 <= Lq, Lq and Lk + prefix <= 256: the Motionformer space attention,
+// 196 x 197): mma.sync m16n8k16 with the fragment idioms of attn_mma_kernel (attention.cu).  One CTA (8 warps) per problem; Q, K, V, dO
+// are staged once in shared memory (144-byte row pitch).
+//   phase 0  D_i = dO_i . O_i                                                     (warp per row)
+//   phase 1  warp = 16 query rows: pass A row log-sum-exp; pass B per 64-key chunk  S -> P,  dP = dO V^T,  dS = P (dP - D),
+//            dQ += dS K  (dS re-used as the A operand straight from its accumulator layout, K^T fragments via ldmatrix.trans)
+//   phase 2  warp = 16 key rows: per 64-query chunk  S^T = K Q^T -> P^T (column statistics from shared memory),  dP^T = V dO^T,
+//            dV += P^T dO,  dK += dS^T Q
+// P and dS enter the second-stage MMAs as bf16 (as in the forward); accumulation is fp32.  Same outputs as the CUDA-core pair above
+// (which stays for the small problems and as the cross-check: desc->impl == 1 forces it).
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int kMmaWarps = 8;
+constexpr int kPitch = 64 * 2 + 16;      // bytes per staged row: ldmatrix rows land on distinct bank groups
+
+// A-operand fragments of 16 consecutive rows starting at row r0 of a staged row-major [row][64] matrix
+__device__ __forceinline__ void load_a_frags(uint32_t base, int r0, int lane, uint32_t (&a)[4][4]) {
+    const uint32_t addr = base + (r0 + (lane & 15)) * kPitch + (lane >> 4) * 16;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(addr + ks * 32, a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
+}
+// acc[2 kb], acc[2 kb + 1] (16 x 16 columns = staged rows c0 + 16 kb ..) += A (16 x 64) * M[rows]^T  for kb < nkb
+__device__ __forceinline__ void mma_a_rowsT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t base, int c0, int nkb, int lane) {
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+        if (kb < nkb) {
+            const uint32_t addr = base + (c0 + kb * 16 + (lane & 7) + ((lane >> 4) << 3)) * kPitch + ((lane >> 3) & 1) * 16;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(addr + ks * 32, b0, b1, b2, b3);
+                mma_bf16_16816(acc[2 * kb], a[ks][0], a[ks][1], a[ks][2], a[ks][3], b0, b1);
+                mma_bf16_16816(acc[2 * kb + 1], a[ks][0], a[ks][1], a[ks][2], a[ks][3], b2, b3);
+            }
+        }
+    }
+}
+// out (16 x 64) += P (16 x 64 columns = staged rows c0 ..; taken from its accumulator layout, rounded to bf16) * M[rows c0 ..] (64 x 64)
+__device__ __forceinline__ void mma_p_rows(float (&out)[8][4], const float (&p)[8][4], uint32_t base, int c0, int nkb, int lane) {
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+        if (kb < nkb) {
+            const uint32_t a0 = pack_bf16x2(p[2 * kb][0], p[2 * kb][1]), a1 = pack_bf16x2(p[2 * kb][2], p[2 * kb][3]);
+            const uint32_t a2 = pack_bf16x2(p[2 * kb + 1][0], p[2 * kb + 1][1]), a3 = pack_bf16x2(p[2 * kb + 1][2], p[2 * kb + 1][3]);
+            const uint32_t addr = base + (c0 + kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + (lane >> 4) * 16;
+#pragma unroll
+            for (int n2 = 0; n2 < 4; ++n2) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(addr + n2 * 32, b0, b1, b2, b3);
+                mma_bf16_16816(out[2 * n2], a0, a1, a2, a3, b0, b1);
+                mma_bf16_16816(out[2 * n2 + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMmaWarps * 32) attn_bwd_mma_kernel(const Desc d, int Lq_pad, int Lk_pad) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const int has_prefix = d.k_prefix != nullptr ? 1 : 0;
+    const int Lkp = d.Lk + has_prefix;
+    const uint32_t sQ = s0, sdO = sQ + Lq_pad * kPitch, sK = sdO + Lq_pad * kPitch, sV = sK + Lk_pad * kPitch;
+    float *lse_s = reinterpret_cast<float *>(smem + (2 * Lq_pad + 2 * Lk_pad) * kPitch);
+    float *delta_s = lse_s + Lq_pad;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    int o, i, h;
+    decode_problem(d, blockIdx.x, o, i, h);
+
+    // ---- stage Q, dO, K, V (prefix key / value first, as in the forward); padding rows are zero so they add nothing to any sum ----
+    {
+        const __nv_bfloat16 *qg = d.q + o * d.q_outer + i * d.q_inner + h * 64, *dog = d.d_o + o * d.o_outer + i * d.o_inner + h * 64;
+        for (int c = tid; c < Lq_pad * 8; c += nthr) {
+            const int r = c >> 3, cc = c & 7;
+            if (r < d.Lq) {
+                cp_async16(sQ + r * kPitch + cc * 16, qg + static_cast<int64_t>(r) * d.q_row + cc * 8);
+                cp_async16(sdO + r * kPitch + cc * 16, dog + static_cast<int64_t>(r) * d.o_row + cc * 8);
+            } else {
+                *reinterpret_cast<uint4 *>(smem + r * kPitch + cc * 16) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(smem + (Lq_pad + r) * kPitch + cc * 16) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * 64, pre_base = o * d.prefix_outer + h * 64;
+        for (int c = tid; c < Lk_pad * 8; c += nthr) {
+            const int r = c >> 3, cc = c & 7;
+            if (r < Lkp) {
+                const bool pre = has_prefix && r == 0;
+                const int64_t off = (pre ? pre_base : kv_base + static_cast<int64_t>(r - has_prefix) * d.kv_row) + cc * 8;
+                cp_async16(sK + r * kPitch + cc * 16, (pre ? d.k_prefix : d.k) + off);
+                cp_async16(sV + r * kPitch + cc * 16, (pre ? d.v_prefix : d.v) + off);
+            } else {
+                *reinterpret_cast<uint4 *>(smem + (2 * Lq_pad + r) * kPitch + cc * 16) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(smem + (2 * Lq_pad + Lk_pad + r) * kPitch + cc * 16) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- phase 0: D_r = dO_r . O_r (O read from global, one warp per row, two elements per lane) ----
+    for (int r = warp; r < Lq_pad; r += kMmaWarps) {
+        float dl = 0.f;
+        if (r < d.Lq) {
+            const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(smem + (Lq_pad + r) * kPitch + lane * 4));
+            const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(d.o + o * d.o_outer + i * d.o_inner + h * 64 + static_cast<int64_t>(r) * d.o_row + lane * 2));
+            dl = a.x * b.x + a.y * b.y;
+        }
+        dl = warp_sum(dl);
+        if (lane == 0) delta_s[r] = dl;
+    }
+    __syncthreads();
+
+    const float sl2 = d.scale_log2;
+    // ---- phase 1: dQ and the row statistics ----
+    for (int q0 = warp * 16; q0 < Lq_pad; q0 += kMmaWarps * 16) {
+        uint32_t qa[4][4], doa[4][4];
+        load_a_frags(sQ, q0, lane, qa);
+        load_a_frags(sdO, q0, lane, doa);
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        for (int kc = 0; kc < Lk_pad; kc += 64) {                 // pass A: log-sum-exp of rows q0 + g, q0 + g + 8
+            const int nkb = min(4, (Lk_pad - kc) >> 4);
+            float s[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+            mma_a_rowsT(s, qa, sK, kc, nkb, lane);
+            float mx0 = m0, mx1 = m1;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const int key = kc + n * 8 + t4 * 2;
+                const bool live = n < 2 * nkb;
+                s[n][0] = (live && key < Lkp) ? s[n][0] * sl2 : -INFINITY;
+                s[n][1] = (live && key + 1 < Lkp) ? s[n][1] * sl2 : -INFINITY;
+                s[n][2] = (live && key < Lkp) ? s[n][2] * sl2 : -INFINITY;
+                s[n][3] = (live && key + 1 < Lkp) ? s[n][3] * sl2 : -INFINITY;
+                mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                ps0 += exp2f(s[n][0] - mx0) + exp2f(s[n][1] - mx0);
+                ps1 += exp2f(s[n][2] - mx1) + exp2f(s[n][3] - mx1);
+            }
+            l0 = l0 * exp2f(m0 - mx0) + ps0;
+            l1 = l1 * exp2f(m1 - mx1) + ps1;
+            m0 = mx0, m1 = mx1;
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        // padded query rows get +inf so that phase 2 sees P = 0 for them
+        const float L0 = q0 + g < d.Lq ? m0 + log2f(l0) : INFINITY, L1 = q0 + g + 8 < d.Lq ? m1 + log2f(l1) : INFINITY;
+        if (t4 == 0) lse_s[q0 + g] = L0, lse_s[q0 + g + 8] = L1;
+        const float D0 = delta_s[q0 + g], D1 = delta_s[q0 + g + 8];
+        float dq[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+        for (int kc = 0; kc < Lk_pad; kc += 64) {                 // pass B
+            const int nkb = min(4, (Lk_pad - kc) >> 4);
+            float s[8][4], dp[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+            mma_a_rowsT(s, qa, sK, kc, nkb, lane);
+            mma_a_rowsT(dp, doa, sV, kc, nkb, lane);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const int key = kc + n * 8 + t4 * 2;
+                const bool live = n < 2 * nkb;
+                const bool v0 = live && key < Lkp, v1 = live && key + 1 < Lkp;
+                s[n][0] = v0 ? exp2f(s[n][0] * sl2 - L0) * (dp[n][0] - D0) : 0.f;
+                s[n][1] = v1 ? exp2f(s[n][1] * sl2 - L0) * (dp[n][1] - D0) : 0.f;
+                s[n][2] = v0 ? exp2f(s[n][2] * sl2 - L1) * (dp[n][2] - D1) : 0.f;
+                s[n][3] = v1 ? exp2f(s[n][3] * sl2 - L1) * (dp[n][3] - D1) : 0.f;
+            }
+            mma_p_rows(dq, s, sK, kc, nkb, lane);                 // dQ += dS K
+        }
+        __nv_bfloat16 *dqg = d.dq + o * d.q_outer + i * d.q_inner + h * 64;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            if (q0 + g < d.Lq)
+                *reinterpret_cast<uint32_t *>(dqg + static_cast<int64_t>(q0 + g) * d.q_row + n * 8 + t4 * 2) = pack_bf16x2(dq[n][0] * d.scale, dq[n][1] * d.scale);
+            if (q0 + g + 8 < d.Lq)
+                *reinterpret_cast<uint32_t *>(dqg + static_cast<int64_t>(q0 + g + 8) * d.q_row + n * 8 + t4 * 2) = pack_bf16x2(dq[n][2] * d.scale, dq[n][3] * d.scale);
+        }
+    }
+    __syncthreads();                                              // lse_s is complete
+
+    // ---- phase 2: dK, dV for 16 staged key rows per warp (staged row 0 is the prefix key when there is one) ----
+    for (int k0 = warp * 16; k0 < Lk_pad; k0 += kMmaWarps * 16) {
+        uint32_t ka[4][4], va[4][4];
+        load_a_frags(sK, k0, lane, ka);
+        load_a_frags(sV, k0, lane, va);
+        const bool kv0 = k0 + g < Lkp, kv1 = k0 + g + 8 < Lkp;
+        float dk[8][4], dv[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+        for (int qc = 0; qc < Lq_pad; qc += 64) {
+            const int nqb = min(4, (Lq_pad - qc) >> 4);
+            float st[8][4], dpt[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) st[n][0] = st[n][1] = st[n][2] = st[n][3] = dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
+            mma_a_rowsT(st, ka, sQ, qc, nqb, lane);               // S^T = K Q^T
+            mma_a_rowsT(dpt, va, sdO, qc, nqb, lane);             // dP^T = V dO^T
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const bool live = n < 2 * nqb;
+                const int qi = qc + n * 8 + t4 * 2;
+                const float La = live ? lse_s[qi] : INFINITY, Lb = live ? lse_s[qi + 1] : INFINITY;
+                const float Da = live ? delta_s[qi] : 0.f, Db = live ? delta_s[qi + 1] : 0.f;
+                const float p0 = kv0 ? exp2f(st[n][0] * sl2 - La) : 0.f, p1 = kv0 ? exp2f(st[n][1] * sl2 - Lb) : 0.f;
+                const float p2 = kv1 ? exp2f(st[n][2] * sl2 - La) : 0.f, p3 = kv1 ? exp2f(st[n][3] * sl2 - Lb) : 0.f;
+                st[n][0] = p0, st[n][1] = p1, st[n][2] = p2, st[n][3] = p3;
+                dpt[n][0] = p0 * (dpt[n][0] - Da), dpt[n][1] = p1 * (dpt[n][1] - Db);
+                dpt[n][2] = p2 * (dpt[n][2] - Da), dpt[n][3] = p3 * (dpt[n][3] - Db);
+            }
+            mma_p_rows(dv, st, sdO, qc, nqb, lane);               // dV += P^T dO
+            mma_p_rows(dk, dpt, sQ, qc, nqb, lane);               // dK += dS^T Q
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = k0 + g + 8 * half;                      // staged key row
+            if (r >= Lkp) continue;
+            if (has_prefix && r == 0) {
+                float *dst = d.dprefix + ((static_cast<int64_t>(i) * d.n_outer + o) * d.n_heads + h) * 2 * 64;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    dst[n * 8 + t4 * 2] = dk[n][2 * half] * d.scale, dst[n * 8 + t4 * 2 + 1] = dk[n][2 * half + 1] * d.scale;
+                    dst[64 + n * 8 + t4 * 2] = dv[n][2 * half], dst[64 + n * 8 + t4 * 2 + 1] = dv[n][2 * half + 1];
+                }
+            } else {
+                const int64_t off = o * d.kv_outer + i * d.kv_inner + h * 64 + static_cast<int64_t>(r - has_prefix) * d.kv_row;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    *reinterpret_cast<uint32_t *>(d.dk + off + n * 8 + t4 * 2) = pack_bf16x2(dk[n][2 * half] * d.scale, dk[n][2 * half + 1] * d.scale);
+                    *reinterpret_cast<uint32_t *>(d.dv + off + n * 8 + t4 * 2) = pack_bf16x2(dv[n][2 * half], dv[n][2 * half + 1]);
+                }
+            }
+        }
     }
 }
 
@@ -431,6 +694,18 @@ extern "C" int sfb_attention_bwd(const sfb_attn_desc *f, const void *d_out, void
     d.scale = f->scale, d.scale_log2 = f->scale * 1.4426950408889634f;
     const int64_t n_prob = static_cast<int64_t>(f->n_outer) * f->n_inner * f->n_heads;
     SFB_CHECK_ARG(n_prob < (1ll << 31), "sfb_attention_bwd: too many problems for one launch");
+    cudaStream_t st0 = reinterpret_cast<cudaStream_t>(stream);
+    // large head-dim-64 problems (space attention): the mma.sync kernel; impl == 1 or SFB_ATTN_BWD_MMA=0 keeps the CUDA-core pair
+    static const bool mma_enabled = !(getenv("SFB_ATTN_BWD_MMA") && atoi(getenv("SFB_ATTN_BWD_MMA")) == 0);
+    const int Lq_pad = (f->Lq + 15) & ~15, Lk_pad = (Lt + 15) & ~15;
+    if (mma_enabled && f->impl != 1 && f->head_dim == 64 && f->Lq >= 64 && Lq_pad <= 256 && Lk_pad <= 256 && f->q_row % 2 == 0 && f->kv_row % 2 == 0) {
+        const size_t smem = static_cast<size_t>(2 * Lq_pad + 2 * Lk_pad) * kPitch + 2 * Lq_pad * sizeof(float);
+        int rc0;
+        if ((rc0 = set_smem(attn_bwd_mma_kernel, smem)) != SFB_OK) return rc0;
+        attn_bwd_mma_kernel<<<static_cast<unsigned>(n_prob), kMmaWarps * 32, smem, st0>>>(d, Lq_pad, Lk_pad);
+        SFB_CHECK_LAUNCH();
+        return SFB_OK;
+    }
     const dim3 g1(static_cast<unsigned>(n_prob), (f->Lq + kRowsPerCta - 1) / kRowsPerCta), g2(static_cast<unsigned>(n_prob), (Lt + kRowsPerCta - 1) / kRowsPerCta);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc;

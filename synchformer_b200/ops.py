@@ -403,8 +403,10 @@ def empty_bf16(shape, device) -> torch.Tensor:
 
 def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, dq: torch.Tensor, dk: torch.Tensor,
                   dv: torch.Tensor, *, q_strides, kv_strides, o_strides, n_outer: int, n_inner: int, n_heads: int, head_dim: int, Lq: int, Lk: int,
-                  scale: float, k_prefix: Optional[torch.Tensor] = None, v_prefix: Optional[torch.Tensor] = None, prefix_outer: int = 0):
+                  scale: float, k_prefix: Optional[torch.Tensor] = None, v_prefix: Optional[torch.Tensor] = None, prefix_outer: int = 0,
+                  impl: int = 0):
     """Backward of `attention(...)` with the same view arguments; d_out is addressed like out, dq / dk / dv like q / k / v.
+    impl: 0 = auto (mma.sync kernel for head_dim 64 and 64 <= Lq, Lk + prefix <= 256; CUDA-core kernels otherwise), 1 = CUDA-core kernels.
     Returns the per-problem prefix gradients (n_inner, n_outer, n_heads, 2, head_dim) fp32 (None without a prefix): sum them over the
     problems that share the prefix row (colsum)."""
     require_cuda(q, 'q')
@@ -419,7 +421,7 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.
     d.o_outer, d.o_inner, d.o_row = o_strides
     d.prefix_outer = prefix_outer
     d.n_outer, d.n_inner, d.n_heads, d.head_dim, d.Lq, d.Lk = n_outer, n_inner, n_heads, head_dim, Lq, Lk
-    d.scale, d.impl = scale, 0
+    d.scale, d.impl = scale, impl
     d.q_extra, d.q_extra_outer, d.extra_partial = None, 0, None
     lib = _lib.load()
     stats = torch.empty((lib.sfb_attention_bwd_stats_floats(ctypes.byref(d)),), device=q.device, dtype=torch.float32)

@@ -115,7 +115,23 @@ def run(front: bool):
     from synchformer_b200._lib import AttnDesc
     D, TOK, h, d = 768, 1569, 12, 64
     row, seg = 3 * D, TOK * 3 * D
-    for n, mode in ((1, 'time'), (1, 'space')):
+    # the mma.sync kernel (Lq >= 64, head_dim 64) on a 2-frame layout whose last key row ends at the guard page, then the CUDA-core pair (impl 1)
+    for impl in (0, 1):
+        rows_ = 2 * 196 + 1
+        qkv, att, d_o = bf16(rows_ * 3 * D, 0.5), bf16(rows_ * D), bf16(rows_ * D)
+        dqkv = out(rows_ * 3 * D * 2)
+        desc = AttnDesc()
+        desc.q, desc.k, desc.v, desc.out = qkv.addr + row * 2, qkv.addr + (row + D) * 2, qkv.addr + (row + 2 * D) * 2, att.addr + D * 2
+        desc.k_prefix, desc.v_prefix, desc.prefix_outer = qkv.addr + D * 2, qkv.addr + 2 * D * 2, rows_ * row
+        desc.q_outer, desc.q_inner, desc.q_row = rows_ * row, 196 * row, row
+        desc.kv_outer, desc.kv_inner, desc.kv_row = rows_ * row, 196 * row, row
+        desc.o_outer, desc.o_inner, desc.o_row = rows_ * D, 196 * D, D
+        desc.n_outer, desc.n_inner, desc.n_heads, desc.head_dim, desc.Lq, desc.Lk, desc.scale, desc.impl = 1, 2, 12, 64, 196, 196, 0.125, impl
+        desc.q_extra, desc.q_extra_outer, desc.extra_partial = None, 0, None
+        ok(lib.sfb_attention_bwd(ctypes.byref(desc), ctypes.c_void_p(d_o.addr + D * 2), ctypes.c_void_p(dqkv.addr + row * 2),
+                                 ctypes.c_void_p(dqkv.addr + (row + D) * 2), ctypes.c_void_p(dqkv.addr + (row + 2 * D) * 2), out(2 * 12 * 2 * 64 * 4).ptr(),
+                                 out(lib.sfb_attention_bwd_stats_floats(ctypes.byref(desc)) * 4).ptr(), None), f'attention bwd space impl={impl}')
+    for n, mode in ((1, 'time'),):
         qkv, att, d_o = bf16(n * TOK * 3 * D, 0.5), bf16(n * TOK * D), bf16(n * TOK * D)
         dqkv = out(n * TOK * 3 * D * 2)
         ctypes.memset(dqkv.addr, 0, dqkv.n_bytes)

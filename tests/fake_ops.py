@@ -229,7 +229,7 @@ def _views(n_outer, n_inner, n_heads, hd):
 
 
 def attention_bwd(q, k, v, out, d_out, dq, dk, dv, *, q_strides, kv_strides, o_strides, n_outer, n_inner, n_heads, head_dim, Lq, Lk, scale,
-                  k_prefix=None, v_prefix=None, prefix_outer=0):
+                  k_prefix=None, v_prefix=None, prefix_outer=0, impl=0):
     """sfb_attention_bwd restated with autograd on the dense definition; prefix gradients are returned per problem."""
     hd = head_dim
     view = _views(n_outer, n_inner, n_heads, hd)

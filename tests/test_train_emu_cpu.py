@@ -77,7 +77,18 @@ def test_results_do_not_depend_on_the_thread_schedule(monkeypatch):
         dqkv = ops.attention_train_bwd(qkv, o, d_out, lse, B, T, h, d, 0.102, 0.1, 5, 2)
         ln = ops.layernorm_bwd(dy, x, gamma, 1e-5)
         head = ops.sync_head_bwd(xh, T, gamma, gamma, 1e-5, W, dl, B)
-        return [o, lse, dqkv, *ln, *head, ops.colsum(big), ops.transpose_bf16(big), ops.gelu_bwd(d_out, d_out), ops.dropout(x, 0.3, 9, 1, residual=dy)]
+        # N1: the mma.sync attention backward (1 frame of 196 x 197 with the CLS prefix, 2 heads) and the CUDA-core pair on a small problem
+        rows_, D_ = 197, 768
+        big_qkv = (torch.randn((rows_, 3 * D_), generator=torch.Generator().manual_seed(4)) * 0.7).to(torch.bfloat16)
+        big_do = torch.randn((rows_, D_), generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
+        outs = []
+        for impl, Lq in ((0, 196), (1, 40)):
+            dq_ = torch.zeros_like(big_qkv)
+            part = ops.attention_bwd(big_qkv[1:], big_qkv[1:, D_:], big_qkv[1:, 2 * D_:], big_do[1:], big_do[1:], dq_[1:], dq_[1:, D_:], dq_[1:, 2 * D_:],
+                                     q_strides=(0, 0, 3 * D_), kv_strides=(0, 0, 3 * D_), o_strides=(0, 0, D_), n_outer=1, n_inner=1, n_heads=2, head_dim=64,
+                                     Lq=Lq, Lk=Lq, scale=0.125, k_prefix=big_qkv[:, D_:], v_prefix=big_qkv[:, 2 * D_:], prefix_outer=0, impl=impl)
+            outs += [dq_, part]
+        return [o, lse, dqkv, *ln, *head, ops.colsum(big), ops.transpose_bf16(big), ops.gelu_bwd(d_out, d_out), ops.dropout(x, 0.3, 9, 1, residual=dy), *outs]
 
     try:
         lib.emu_set_schedule(0, 0)

@@ -182,3 +182,40 @@ def test_shifted_window_eval_host_logic(monkeypatch, B, S, W):
     pa, pv = avclip.shift_and_get_preds(a, v, W)
     ra, rv, _ = O.shift_and_get_preds(a, v, W)
     assert pa.shape == (B, S - W + 1) and torch.equal(pa, ra) and torch.equal(pv, rv)
+
+
+@pytest.mark.parametrize('Lq,Lk,prefix', [(196, 196, True), (64, 100, True), (130, 77, False)])
+def test_mma_attention_backward_matches_cuda_core_kernels_and_autograd(monkeypatch, Lq, Lk, prefix):
+    """sfb_attention_bwd: the mma.sync kernel (large head-dim-64 problems) against the CUDA-core kernel pair (impl = 1) and against autograd of
+    the dense definition, on the emulator; sizes that are not multiples of 16 exercise the padding / masking."""
+    lib = binding.install(monkeypatch)
+    from synchformer_b200 import ops
+    torch.manual_seed(Lq + Lk)
+    D, hd, heads, n_inner = 768, 64, 2, 2
+    rows = n_inner * max(Lq, Lk) + 1
+    qkv = (torch.randn(rows, 3 * D) * 0.7).to(torch.bfloat16)
+    d_o = torch.randn(rows, D).to(torch.bfloat16)
+    row = 3 * D
+    kw = dict(q_strides=(rows * row, Lq * row, row), kv_strides=(rows * row, Lk * row, row), o_strides=(rows * D, Lq * D, D), n_outer=1, n_inner=n_inner,
+              n_heads=heads, head_dim=hd, Lq=Lq, Lk=Lk, scale=0.125)
+    pk = dict(k_prefix=qkv[:, D:], v_prefix=qkv[:, 2 * D:], prefix_outer=rows * row) if prefix else {}
+    att = torch.zeros(rows, D, dtype=torch.bfloat16)
+    monkeypatch.setattr(fake_ops, 'REAL_DTYPES', True)
+    fake_ops.attention(qkv[1:], qkv[1:, D:], qkv[1:, 2 * D:], att[1:], **kw, **pk)
+    res = {}
+    for name, impl in (('mma', 0), ('cuda', 1)):
+        dqkv = torch.zeros_like(qkv)
+        before = lib.emu_launch_count()
+        part = ops.attention_bwd(qkv[1:], qkv[1:, D:], qkv[1:, 2 * D:], att[1:], d_o[1:], dqkv[1:], dqkv[1:, D:], dqkv[1:, 2 * D:], impl=impl, **kw, **pk)
+        res[name] = (dqkv, part, lib.emu_launch_count() - before)
+    assert res['mma'][2] == 1 and res['cuda'][2] == 2                     # one fused launch vs the two-pass pair
+    ref = torch.zeros_like(qkv)
+    ref_part = fake_ops.attention_bwd(qkv[1:], qkv[1:, D:], qkv[1:, 2 * D:], att[1:], d_o[1:], ref[1:], ref[1:, D:], ref[1:, 2 * D:], **kw, **pk)
+    cols = torch.cat([torch.arange(heads * hd) + k * D for k in range(3)])
+    r = ref[:, cols].float()
+    for name in ('mma', 'cuda'):
+        g = res[name][0][:, cols].float()
+        assert float((g - r).norm() / r.norm()) < 6e-3, name
+        if prefix:
+            assert float((res[name][1] - ref_part).norm() / ref_part.norm()) < 6e-3, name
+    assert float((res['mma'][0][:, cols].float() - res['cuda'][0][:, cols].float()).norm() / r.norm()) < 6e-3
