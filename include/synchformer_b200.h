@@ -95,7 +95,7 @@ typedef struct sfb_attn_desc {
      * that outer index; its softmax state over that problem's keys (the prefix key is counted for inner == 0 only) goes to
      *   extra_partial[((o*n_heads + h)*n_inner + i)*(head_dim + 2)] = { max (log2 units), sum, out[head_dim] / sum }   (fp32)
      * and sfb_attention_merge_partials() combines the n_inner states.  NULL = off.  Supported where
-     * sfb_attention_extra_supported() says so (the tcgen05 space-attention kernel). */
+     * sfb_attention_extra_supported() says so (the tcgen05 space-attention kernel; with SFB_TIME_CLS_FUSED=1 also the time-attention kernel). */
     const void *q_extra;
     int64_t q_extra_outer;
     float *extra_partial;

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(HD == 64 ? 512 : 416) attn_mma_kernel(const De
 // staged with cp.async (fully coalesced 1.5 KB row pieces), and the two 8 x 9 attentions of a pair are evaluated as ONE block-
 // diagonal m16n8k16 problem: S = [Q_a; Q_b] [K_a | K_b | k_cls]^T keeps the two diagonal 8 x 8 blocks and the CLS column,
 // O = P V with P zero off the diagonal blocks.  28 mma.sync per (pair, head) instead of 2 x 9 x 64 x 2 x 8 CUDA-core FMAs.
-template <int H>   // heads == warps per CTA
+template <int H, bool kExtra = false>   // heads == warps per CTA; kExtra: also serve the fused extra (CLS) query, see the end of the kernel
 __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) {
     constexpr int HD = 64;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -567,6 +567,37 @@ __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) 
             }
         }
     }
+    if (kExtra) {
+        // Fused extra query (the Motionformer CLS query of the time attention, vit_helper.py:124): one more query row per (outer, head)
+        // that attends to ALL keys of its outer index.  This CTA holds the 8 keys / values of its two locations (and the CLS key / value):
+        // per head it emits the query's softmax state over each location's keys - { max (log2 units), sum, out / sum } - to
+        // xpartial[((o * H + head) * n_inner + location) * 66]; the CLS key is counted for location 0 only; sfb_attention_merge_partials
+        // combines the n_inner states.  17 dot products of 64 per warp on the CUDA cores: nothing next to the HBM traffic of the kernel.
+        const float2 qx = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(d.xq + o * d.xq_outer + warp * HD + lane * 2));
+        const uint8_t *kbase = smem + warp * (HD * 2) + seg_bytes, *vbase = kbase + seg_bytes;
+        const uint8_t *kcls = smem + cls_off + warp * (HD * 2), *vcls = kcls + seg_bytes;
+        float sc = 0.f;
+        for (int j = 0; j < 17; ++j) {
+            const float2 kk = unpack_bf16x2(*reinterpret_cast<const uint32_t *>((j < 16 ? kbase + j * PITCH : kcls) + lane * 4));
+            const float p = warp_sum(qx.x * kk.x + qx.y * kk.y);
+            if (lane == j) sc = p * sl2;
+        }
+        const bool in_a = lane < 8 || (lane == 16 && i0p == 0), in_b = lane >= 8 && lane < 16;
+        const float ma = warp_max(in_a ? sc : -INFINITY), mb = warp_max(in_b ? sc : -INFINITY);
+        const float pa = in_a ? exp2f(sc - ma) : 0.f, pb = in_b ? exp2f(sc - mb) : 0.f;
+        const float la = warp_sum(pa), lb = warp_sum(pb);
+        float2 oa = make_float2(0.f, 0.f), ob = make_float2(0.f, 0.f);
+        for (int j = 0; j < 17; ++j) {
+            const float wa = __shfl_sync(0xffffffffu, pa, j), wb = __shfl_sync(0xffffffffu, pb, j);
+            const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t *>((j < 16 ? vbase + j * PITCH : vcls) + lane * 4));
+            oa.x = fmaf(wa, vv.x, oa.x), oa.y = fmaf(wa, vv.y, oa.y);
+            ob.x = fmaf(wb, vv.x, ob.x), ob.y = fmaf(wb, vv.y, ob.y);
+        }
+        float *dst_a = d.xpartial + ((static_cast<int64_t>(o) * H + warp) * d.n_inner + i0p) * (HD + 2), *dst_b = dst_a + (HD + 2);
+        if (lane == 0) dst_a[0] = ma, dst_a[1] = la, dst_b[0] = mb, dst_b[1] = lb;
+        dst_a[2 + 2 * lane] = oa.x / la, dst_a[3 + 2 * lane] = oa.y / la;
+        dst_b[2 + 2 * lane] = ob.x / lb, dst_b[3 + 2 * lane] = ob.y / lb;
+    }
 }
 
 }  // namespace attn
@@ -598,15 +629,25 @@ static bool sfb_attn_aligned16(const sfb_attn_desc *d) {
            ((d->q_outer | d->q_inner | d->q_row | d->kv_outer | d->kv_inner | d->kv_row | d->o_outer | d->o_inner | d->o_row | d->prefix_outer) % 8) == 0;
 }
 
+static bool sfb_time_extra_supported(const sfb_attn_desc *desc);
+
 extern "C" int sfb_attention_extra_supported(const sfb_attn_desc *desc) {
     using namespace sfb::attn;
     if (desc == nullptr || desc->impl != 0 || desc->head_dim != 64 || !sfb_attn_aligned16(desc)) return 0;
+    if (sfb_time_extra_supported(desc)) return 1;
     if (getenv("SFB_ATTN_TC") && atoi(getenv("SFB_ATTN_TC")) == 0) return 0;
     if (getenv("SFB_ATTN_TC_VARIANT") && atoi(getenv("SFB_ATTN_TC_VARIANT")) != 1) return 0;
     if ((reinterpret_cast<uintptr_t>(desc->q_extra) & 15) != 0 || desc->q_extra_outer % 8 != 0) return 0;
     Desc d = {};
     d.Lq = desc->Lq, d.Lk = desc->Lk, d.has_prefix = desc->k_prefix != nullptr;
     return tc_supported(d) && desc->Lq < 256 ? 1 : 0;     // the extra query occupies query row Lq of the second 128-row tile
+}
+
+// the block-diagonal time-attention kernel can serve the extra query too; opt-in (SFB_TIME_CLS_FUSED=1) until measured on hardware
+static bool sfb_time_extra_supported(const sfb_attn_desc *desc) {
+    static const bool enabled = getenv("SFB_TIME_CLS_FUSED") && atoi(getenv("SFB_TIME_CLS_FUSED")) == 1;
+    return enabled && desc->impl == 0 && desc->head_dim == 64 && desc->Lq == 8 && desc->Lk == 8 && desc->k_prefix != nullptr && desc->n_inner % 2 == 0 &&
+           desc->n_heads == 12 && sfb_attn_aligned16(desc) && (reinterpret_cast<uintptr_t>(desc->q_extra) & 15) == 0 && desc->q_extra_outer % 8 == 0;
 }
 
 extern "C" int sfb_attention_merge_partials(const float *partial, void *out, int64_t out_outer, int n_outer, int n_inner, int n_heads, int head_dim,
@@ -703,12 +744,16 @@ extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
         constexpr int smem_bytes = 16 * (3 * seg_bytes + 16) + 2 * seg_bytes + 16;       // 77 KB: two CTAs per SM
         static bool attr_set = false;
         if (!attr_set) {
-            SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_time_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_time_mma_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_time_mma_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
             attr_set = true;
         }
         const int64_t n_pairs = static_cast<int64_t>(d.n_outer) * (d.n_inner / 2);
         SFB_CHECK_ARG(n_pairs < (1ll << 31), "sfb_attention: too many problems");
-        attn_time_mma_kernel<H><<<static_cast<unsigned>(n_pairs), 32 * H, smem_bytes, st>>>(d);
+        if (d.xq != nullptr)
+            attn_time_mma_kernel<H, true><<<static_cast<unsigned>(n_pairs), 32 * H, smem_bytes, st>>>(d);
+        else
+            attn_time_mma_kernel<H, false><<<static_cast<unsigned>(n_pairs), 32 * H, smem_bytes, st>>>(d);
         SFB_CHECK_LAUNCH();
         return SFB_OK;
     }

@@ -176,7 +176,8 @@ class MotionFormer(_KernelModule):
         if mode == 'time':    # '(b n) f d': 8 frames of one location + CLS key/value
             fused = ops.attention(q1, k1, v1, o1, q_strides=(seg, row, V_SPACE * row), kv_strides=(seg, row, V_SPACE * row),
                                   o_strides=(V_TOK * D, D, V_SPACE * D), n_outer=n, n_inner=V_SPACE, n_heads=12, head_dim=64, Lq=V_FRAMES,
-                                  Lk=V_FRAMES, scale=0.125, k_prefix=k, v_prefix=v, prefix_outer=seg)
+                                  Lk=V_FRAMES, scale=0.125, k_prefix=k, v_prefix=v, prefix_outer=seg,
+                                  q_extra=q, q_extra_outer=seg, extra_out=att, extra_out_outer=V_TOK * D)    # fused only with SFB_TIME_CLS_FUSED=1
         else:                 # '(b f) n d': 196 locations of one frame + CLS key/value; the CLS query rides along (fused) when supported
             fused = ops.attention(q1, k1, v1, o1, q_strides=(seg, V_SPACE * row, row), kv_strides=(seg, V_SPACE * row, row),
                                   o_strides=(V_TOK * D, V_SPACE * D, D), n_outer=n, n_inner=V_FRAMES, n_heads=12, head_dim=64, Lq=V_SPACE,

@@ -196,3 +196,27 @@ def test_emulated_mma_attention_kernels_match_the_dense_definition(monkeypatch):
                              Lq=1, Lk=TOK, scale=0.125)) < 8e-3                                                # attn_row1_kernel
     assert run(n * TOK, dict(q_strides=(seg, 196 * row, row), kv_strides=(seg, 196 * row, row), o_strides=(TOK * D, 196 * D, D), n_outer=n, n_inner=8,
                              n_heads=12, head_dim=64, Lq=196, Lk=196, scale=0.125), q_off=1, prefix=seg) < 8e-3     # space: attn_mma_kernel<64>
+
+
+def test_time_attention_cls_query_default_and_fused_variant(monkeypatch):
+    """MotionFormer._divided_attention(mode='time') on the emulated real kernels: the default path (time kernel + single-query kernel for the
+    CLS row, both hardware-verified) and, in a subprocess with SFB_TIME_CLS_FUSED=1, the opt-in variant in which the CLS query rides along
+    in the time kernel and is merged from per-location softmax states (tests/emu/time_cls_fused_check.py)."""
+    import subprocess
+    import sys
+    lib = binding.install(monkeypatch)
+    from synchformer_b200 import model as M
+    torch.manual_seed(0)
+    n, D, TOK = 1, 768, 1569
+    qkv = (torch.randn(n * TOK, 3 * D) * 0.7).to(torch.bfloat16)
+    att, want = torch.zeros(n * TOK, D, dtype=torch.bfloat16), torch.zeros(n * TOK, D, dtype=torch.bfloat16)
+    m = M.MotionFormer.__new__(M.MotionFormer)
+    before = lib.emu_launch_count()
+    M.MotionFormer._divided_attention(m, qkv, att, n, 'time')
+    assert lib.emu_launch_count() - before == 2                       # time kernel + attn_row1_kernel
+    fake_ops.install(monkeypatch, round_bf16=True, names=('attention',), real_dtypes=True)
+    M.MotionFormer._divided_attention(m, qkv, want, n, 'time')
+    assert (att.float() - want.float()).abs().max() < 1.6e-2
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu', 'time_cls_fused_check.py')
+    r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=900, env=dict(os.environ, SFB_TIME_CLS_FUSED='1'))
+    assert r.returncode == 0 and r.stdout.strip().endswith('OK'), (r.returncode, r.stdout[-400:], r.stderr[-1500:])
