@@ -698,7 +698,8 @@ extern "C" int sfb_attention_bwd(const sfb_attn_desc *f, const void *d_out, void
     // large head-dim-64 problems (space attention): the mma.sync kernel; impl == 1 or SFB_ATTN_BWD_MMA=0 keeps the CUDA-core pair
     static const bool mma_enabled = !(getenv("SFB_ATTN_BWD_MMA") && atoi(getenv("SFB_ATTN_BWD_MMA")) == 0);
     const int Lq_pad = (f->Lq + 15) & ~15, Lk_pad = (Lt + 15) & ~15;
-    if (mma_enabled && f->impl != 1 && f->head_dim == 64 && f->Lq >= 64 && Lq_pad <= 256 && Lk_pad <= 256 && f->q_row % 2 == 0 && f->kv_row % 2 == 0) {
+    const bool al4 = ((reinterpret_cast<uintptr_t>(f->out) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 3) == 0;
+    if (mma_enabled && f->impl != 1 && f->head_dim == 64 && f->Lq >= 64 && Lq_pad <= 256 && Lk_pad <= 256 && al4) {      // 4-byte O loads / gradient stores
         const size_t smem = static_cast<size_t>(2 * Lq_pad + 2 * Lk_pad) * kPitch + 2 * Lq_pad * sizeof(float);
         int rc0;
         if ((rc0 = set_smem(attn_bwd_mma_kernel, smem)) != SFB_OK) return rc0;
