@@ -220,3 +220,6 @@ def test_time_attention_cls_query_default_and_fused_variant(monkeypatch):
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu', 'time_cls_fused_check.py')
     r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=900, env=dict(os.environ, SFB_TIME_CLS_FUSED='1'))
     assert r.returncode == 0 and r.stdout.strip().endswith('OK'), (r.returncode, r.stdout[-400:], r.stderr[-1500:])
+
+
+test_gradients_scale_exactly_with_the_loss_scale_at_config4_size = G.test_gradients_scale_exactly_with_the_loss_scale_at_config4_size

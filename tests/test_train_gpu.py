@@ -355,3 +355,21 @@ def test_fused_cross_entropy_and_adam(cuda_device):
     norm, found = a.step(grad_scale=1.0, max_norm=1.0)
     assert float(found) == 1.0 and all(torch.equal(p, q) for p, q in zip(mine, before))
     assert float(a._dev_state[0]['step']) == 4.0
+
+
+def test_gradients_scale_exactly_with_the_loss_scale_at_config4_size(cuda_device, monkeypatch):
+    """Size-independent property at BASELINE config 4's per-GPU size (32 clips x 14 segments, T = 198, M = 6336 rows): the backward is
+    linear in the upstream gradient, and a power-of-two loss scale (what GradScaler applies) commutes with every bf16 / fp32 rounding in
+    it, so gradients under scale 2^12 are bit-for-bit 2^12 times the unscaled ones.  Same seed -> same masks."""
+    B, S = (32, 14) if cuda_device.type == 'cuda' else (2, 3)
+    torch.manual_seed(8)
+    sd = synth.synthetic_state_dict(1337, n_segments=S)
+    model = _train_model(S, 0.1, sd, cuda_device)
+    vf, af = (torch.randn((B, S, 8, D)) * 0.5).to(cuda_device), (torch.randn((B, S, 6, D)) * 0.5).to(cuda_device)
+    targets = torch.randint(0, 21, (B,)).to(cuda_device)
+    _, logits1, g1 = _step(model, vf, af, targets, 99, monkeypatch, loss_scale=1.0)
+    _, logits2, g2 = _step(model, vf, af, targets, 99, monkeypatch, loss_scale=4096.0)
+    assert torch.equal(logits1, logits2)
+    assert all(torch.isfinite(g).all() for g in g2.values())
+    for n in g1:
+        assert torch.equal(g1[n] * 4096.0, g2[n]), n
