@@ -162,7 +162,8 @@ def build(force: bool = False) -> str:
                  'namespace sfb { namespace attn { bool tc_supported(const Desc &) { return false; } '
                  'int launch_tc(const Desc &, cudaStream_t) { return SFB_E_UNSUPPORTED; } } }\n'
                  'extern "C" void emu_set_schedule(int mode, unsigned long long seed) { emu::schedule() = mode; emu::rng() = seed * 2 + 1; }\n')
-    cmd = ['g++', '-O2', '-g', '-std=c++17', '-shared', '-fPIC', '-w', '-I', OUT, '-I', CSRC, '-I', CUDA_INC, '-o', LIB] + gen + [extra]
+    cmd = ['g++', '-O2', '-g', '-std=c++17', '-shared', '-fPIC', '-w', '-fno-strict-aliasing',   # CUDA code type-puns freely; nvcc does not assume strict aliasing
+           '-I', OUT, '-I', CSRC, '-I', CUDA_INC, '-o', LIB] + gen + [extra]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('emulator build failed:\n' + r.stdout + r.stderr)

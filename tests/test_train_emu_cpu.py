@@ -156,6 +156,27 @@ def test_emulator_reproduces_kernels_that_are_verified_on_hardware(monkeypatch):
     want = fake_ops.im2col_video((vis.float() / 255.0 - 0.5) / 0.5)
     assert (ops.im2col_video(vis).float() - want.float()).abs().max() < 1e-2                       # uint8 path: normalisation fused into the gather
     assert torch.equal(ops.im2col_video(vis.float()), fake_ops.im2col_video(vis.float()))
+    half = ((vis.float() / 255.0 - 0.5) / 0.5).half()
+    assert torch.equal(ops.im2col_video(half), fake_ops.im2col_video(half.float()))                 # fp16 frames (RGBToHalfToZeroOne)
+
+
+@pytest.mark.skipif(os.environ.get('SFB_EMU_FULL') != '1', reason='~90 s of SIMT emulation; SFB_EMU_FULL=1 runs it (passed when written: 1.4e-2)')
+def test_whole_inference_forward_on_emulated_kernels(monkeypatch):
+    """Synchformer.forward (1 clip x 1 segment, fp16 video) with every kernel except the tcgen05 ones running from its real source on the
+    emulator: 291 launches, logits within the GPU gate of the fp32 oracle (the B200 measured 1.5e-2 on the same path)."""
+    from oracle import synchformer_oracle as O
+    from synchformer_b200 import model as M, synth
+    lib = binding.install(monkeypatch)
+    sd = synth.synthetic_state_dict(1337, n_segments=1)
+    vis = synth.synthetic_video(1, 1, 0).half()
+    aud = O.mel_frontend(synth.synthetic_waveform(1, 1, 0)).float().unsqueeze(2)
+    model = M.build_synchformer(n_segments=1, state_dict=sd)
+    before = lib.emu_launch_count()
+    with torch.no_grad():
+        _, logits = model(vis, aud)
+    _, ref = O.forward(sd, vis.float(), aud)
+    assert lib.emu_launch_count() - before > 250
+    assert (logits - ref).abs().max() < 2e-2 and torch.equal(logits.argmax(-1), ref.argmax(-1))
 
 
 def test_emulated_mma_attention_kernels_match_the_dense_definition(monkeypatch):
