@@ -106,7 +106,7 @@ def test_ast_tower_on_emulated_kernels(setup, monkeypatch):
     _check_bf16(grads, rg, 'afeat_extractor.')
 
 
-@pytest.mark.skipif(os.environ.get('SFB_EMU_FULL') != '1', reason='~5 min of SIMT emulation; SFB_EMU_FULL=1 runs it (passed when written)')
+@pytest.mark.skipif(os.environ.get('SFB_EMU_FULL') != '1', reason='~12 min of SIMT emulation (all kernels but the GEMM from real sources); SFB_EMU_FULL=1 runs it (passed when written)')
 def test_motionformer_tower_on_emulated_kernels(setup, monkeypatch):
     binding.install(monkeypatch)
     loss, vf, af, grads = _product_grads(setup, towers=('v',))
