@@ -13,6 +13,7 @@ timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytes
 echo "memcheck rc=$?" | tee -a $O/summary_train.txt
 timeout 300 python tools/train_bench.py --batch 32 --segments 14 --steps 5 --warmup 3 2>&1 | tail -3 > $O/train_bench_sync_n1.json; echo "sync train bench rc=$?" | tee -a $O/summary_train.txt
 timeout 600 python tools/train_bench.py --mode avclip --batch 8 --segments 8 --steps 3 --warmup 2 2>&1 | tail -3 > $O/train_bench_avclip_n1.json; echo "avclip train bench rc=$?" | tee -a $O/summary_train.txt
+timeout 300 python tools/train_bench.py --mode avclip_fwd --batch 16 --segments 8 --steps 5 --warmup 3 2>&1 | tail -3 > $O/bench_avclip_fwd_n1.json; echo "avclip fwd bench (config 3) rc=$?" | tee -a $O/summary_train.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/train_launches.csv \
     python tools/train_bench.py --batch 8 --segments 14 --steps 1 --warmup 1 > $O/train_ncu.log 2>&1
 python tools/summarize_launches.py $O/train_launches.csv > $O/train_launches_summary.txt 2>&1 || true

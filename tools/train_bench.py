@@ -31,7 +31,7 @@ def main():
     ap.add_argument('--segments', type=int, default=14)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--mode', default='sync', choices=['sync', 'avclip'], help="sync: BASELINE config 4 (stage II, frozen extractors); "
+    ap.add_argument('--mode', default='sync', choices=['sync', 'avclip', 'avclip_fwd'], help="sync: BASELINE config 4 (stage II, frozen extractors); "
                     "avclip: stage-I contrastive step (both encoders train, SURVEY.md 8f N1; --batch x --segments segments per GPU)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
@@ -45,6 +45,8 @@ def main():
     torch.manual_seed(1337 + rank)
     if args.mode == 'avclip':
         return avclip_bench(args, rank, world, local, dev)
+    if args.mode == 'avclip_fwd':
+        return avclip_forward_bench(args, rank, world, local, dev)
     model = M.build_synchformer(n_segments=S, state_dict=synth.synthetic_state_dict(1337, n_segments=S), device=dev)
     for ext in (model.vfeat_extractor, model.afeat_extractor):            # get_model: is_trainable False (train_utils.py:199-204)
         ext.requires_grad_(False)
@@ -188,6 +190,46 @@ def avclip_bench(args, rank, world, local, dev):
             'scaling': 'weak', 'config': {'workload': f'segment_avclip.yaml training step, {B} x {S} segments/GPU', 'optimizer': 'torch.optim.AdamW'},
             'split_ms': {k: mean(v) for k, v in ev.items()}, 'gpu_launches_per_step': (ops.launch_count() - n0) / args.steps, 'loss': float(loss),
             'peak_mem_gb': torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def avclip_forward_bench(args, rank, world, local, dev):
+    """BASELINE config 3: segment_avclip.yaml contrastive FORWARD (AST + Motionformer, time-average pooled, similarity + CE), eval / no_grad,
+    --batch x --segments segments per GPU (16 x 8 = 128 in the config)."""
+    from synchformer_b200 import avclip, ops, synth
+    B, S = args.batch, args.segments
+    model = avclip.AVCLIP().to(dev).eval()
+    sd = synth.synthetic_state_dict(1337, n_segments=S)
+    model.v_encoder.load_state_dict({k[len('vfeat_extractor.'):]: v for k, v in sd.items() if k.startswith('vfeat_extractor.')})
+    model.a_encoder.load_state_dict({k[len('afeat_extractor.'):]: v for k, v in sd.items() if k.startswith('afeat_extractor.')})
+    g = torch.Generator(device=dev).manual_seed(rank)
+    rgb = (torch.rand((B, S, 3, 16, 224, 224), device=dev, generator=g, dtype=torch.float16) - 0.5) / 0.5
+    aud = torch.randn((B, S, 66, 128), device=dev, generator=g)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = model(rgb, aud)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n0 = ops.launch_count()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            out = model(rgb, aud)
+        t1.record()
+        torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'segments/sec stage-I contrastive forward (BASELINE config 3)', 'value': B * S * world / (float(ms) / 1e3), 'unit': 'segments/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(ms), 'dtype': 'bf16', 'data': 'synthetic', 'scaling': 'weak',
+            'config': {'workload': f'segment_avclip.yaml contrastive forward, {B} x {S} segments/GPU'},
+            'gpu_launches_per_step': (ops.launch_count() - n0) / args.steps, 'loss': float(out['losses']['segment_contrastive_loss']),
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
