@@ -253,6 +253,30 @@ int sfb_droppath(const float *in, const float *residual, void *out, int out_bf16
  * sfb_layernorm without the normalisation (patch-token gradients without the CLS rows, fp32 -> bf16 GEMM operands). */
 int sfb_gather_rows_bf16(const float *in, int64_t ld, void *out, int rows, int group, int group_stride, int offset, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * N1, tail of the stage-I contrastive step: AVCLIP.forward after the two towers (open_clip/model.py:489-527, 536-545;
+ * AveragePooling motionformer.py:405-409).  All tensors fp32, contiguous; deterministic (no atomics).
+ * --------------------------------------------------------------------------------------------------------- */
+/* out (n, D) = mean over the T token rows of x (n, T, D)  ['BS T D -> BS D'];  backward: dx (n, T, D) = dout / T */
+int sfb_mean_tokens(const float *x, float *out, int n, int T, int D, void *stream);
+int sfb_mean_tokens_bwd(const float *dout, float *dx, int n, int T, int D, void *stream);
+/* F.normalize(x, dim=-1): xn = x / max(|x|, 1e-12); inv_norm (n) is kept for the backward dx = (dxn - xn (xn . dxn)) * inv_norm */
+int sfb_l2_normalize(const float *x, float *xn, float *inv_norm, int n, int D, void *stream);
+int sfb_l2_normalize_bwd(const float *xn, const float *inv_norm, const float *dxn, float *dx, int n, int D, void *stream);
+/* compute_loss (open_clip/model.py:507-527): sim_v2a = vn an_all^T / scale, sim_a2v = an vn_all^T / scale with the n local rows as
+ * queries and the N >= n gathered rows as keys (N = n without gather_for_loss), targets eye(n, N) exactly as the reference builds them,
+ * loss[0] = (CE(sim_v2a) + CE(sim_a2v)) / 2.  scale: DEVICE pointer to the (clamped) logit_scale parameter - no host read.
+ * Also written: dscale[0] = d loss / d scale, G (2, n, N) = d loss / d sim for the two directions (input of the backward).
+ * row_ws: 4 n floats of scratch.  N <= 8192, D <= 4096. */
+int sfb_contrastive_loss(const float *vn, const float *an, const float *vn_all, const float *an_all, int n, int N, int D, const float *scale,
+                         float *loss, float *dscale, float *G, float *row_ws, void *stream);
+/* gradients of the loss times the DEVICE scalar upstream[0] (the GradScaler's scale): local query rows d_vn / d_an (n, D), gathered key
+ * rows d_vn_all / d_an_all (N, D) - reduce-scatter them over the ranks and add; pass NULL for both when N == n and the keys ARE the
+ * queries (no gathering): their gradient is then added into d_vn / d_an.  dscale_out[0] = dscale[0] * upstream[0]. */
+int sfb_contrastive_loss_bwd(const float *vn, const float *an, const float *vn_all, const float *an_all, const float *G, int n, int N, int D,
+                             const float *scale, const float *upstream, const float *dscale, float *d_vn, float *d_an, float *d_vn_all,
+                             float *d_an_all, float *dscale_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

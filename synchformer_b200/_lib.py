@@ -80,6 +80,15 @@ SIGNATURES = {
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     'sfb_droppath': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_uint64, c_uint32, c_void_p]),
     'sfb_gather_rows_bf16': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    # N1: contrastive tail
+    'sfb_mean_tokens': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'sfb_mean_tokens_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'sfb_l2_normalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'sfb_l2_normalize_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'sfb_contrastive_loss': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    'sfb_contrastive_loss_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

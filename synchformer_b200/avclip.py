@@ -26,13 +26,15 @@ class DoNothingBridge(nn.Identity):
 
 
 def _tower_from_config(cfg, default_cls):
-    """`{target, params[, is_trainable]}` (segment_avclip.yaml:12-44) -> kernel-backed tower.  `ckpt_path` (pre-trained initialisation from
-    HF / a local .pyth) is harness work: it is dropped with a warning, load the weights with `load_state_dict`."""
+    """`{target, params[, is_trainable]}` (segment_avclip.yaml:12-44) -> kernel-backed tower.  A stage-I `.pt` `ckpt_path` initialises the
+    tower (model._init_from_stage1_ckpt); the downloadable pre-trained initialisations (HF hub name / SSv2 .pyth) are dropped with a warning."""
     if cfg is None:
         return None
     params = dict(cfg.get('params', {}) or {})
-    if params.pop('ckpt_path', None) is not None:
-        logging.warning('synchformer_b200.AVCLIP: ckpt_path is ignored - initialise the towers with load_state_dict')
+    if params.get('ckpt_path') is not None and not str(params['ckpt_path']).endswith('.pt'):
+        # the public pre-trained initialisations (HF AudioSet AST, SSv2 Motionformer .pyth) are downloads: no network here
+        logging.warning(f"synchformer_b200.AVCLIP: ckpt_path={params['ckpt_path']!r} is ignored - initialise the towers with load_state_dict")
+        params.pop('ckpt_path')
     name = str(cfg['target']).rsplit('.', 1)[-1]
     if name != default_cls.__name__:
         raise NotImplementedError(f"tower target {cfg['target']} is outside the B200 hot path (expected ...{default_cls.__name__})")

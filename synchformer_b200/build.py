@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libsynchformer_b200.so')
-SOURCES = ['runtime.cu', 'gemm_tcgen05.cu', 'layernorm.cu', 'attention.cu', 'attention_tc.cu', 'embed.cu', 'mel.cu', 'train.cu', 'attention_train.cu', 'attention_bwd.cu', 'optim.cu']
+SOURCES = ['runtime.cu', 'gemm_tcgen05.cu', 'layernorm.cu', 'attention.cu', 'attention_tc.cu', 'embed.cu', 'mel.cu', 'train.cu', 'attention_train.cu', 'attention_bwd.cu', 'optim.cu', 'contrastive.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']
 

@@ -742,11 +742,10 @@ extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
         constexpr int H = 12;
         constexpr int seg_bytes = H * 64 * 2;
         constexpr int smem_bytes = 16 * (3 * seg_bytes + 16) + 2 * seg_bytes + 16;       // 77 KB: two CTAs per SM
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_once;
+        if (attr_once.first()) {
             SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_time_mma_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
             SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_time_mma_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-            attr_set = true;
         }
         const int64_t n_pairs = static_cast<int64_t>(d.n_outer) * (d.n_inner / 2);
         SFB_CHECK_ARG(n_pairs < (1ll << 31), "sfb_attention: too many problems");

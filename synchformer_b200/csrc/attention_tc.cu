@@ -555,11 +555,8 @@ bool tc_supported(const Desc &d) {
 }
 
 int launch_tc(const Desc &d, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC));
     const int64_t n_prob = static_cast<int64_t>(d.n_outer) * d.n_inner * d.n_heads;
     SFB_CHECK_ARG(n_prob < (1ll << 31), "sfb_attention: too many problems");
     // TMA staging needs every problem's rows on one regular 2D grid: outer / inner strides must be whole rows
@@ -582,11 +579,8 @@ int launch_tc(const Desc &d, cudaStream_t st) {
     }
     static const int variant = getenv("SFB_ATTN_TC_VARIANT") ? atoi(getenv("SFB_ATTN_TC_VARIANT")) : 1;   // 1 = persistent (default: measured 2.2 vs 3.0 ms), 2 = two CTAs per SM
     if (use_tma && variant == 2 && d.xq == nullptr) {
-        static bool attr2 = false;
-        if (!attr2) {
-            SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC2));
-            attr2 = true;
-        }
+        static PerDeviceOnce attr_once2;
+        if (attr_once2.first()) SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC2));
         attn_space_tc2_kernel<<<static_cast<unsigned>(n_prob), kThreadsTc2, SMEM_TC2, st>>>(tq, tk, tv, d, qo, qi, ko, ki);
         SFB_CHECK_LAUNCH();
         return SFB_OK;

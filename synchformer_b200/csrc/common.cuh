@@ -33,7 +33,14 @@ void set_error(const char *fmt, ...);
 
 #define SFB_CHECK_LAUNCH() SFB_CHECK_CUDA(cudaGetLastError())
 
-int num_sms();
+int num_sms();           // SM count of the CURRENT device (cached per device ordinal)
+// One-time-per-device setup (cudaFuncSetAttribute, constant tables ...): `once.first()` is true exactly once for each device
+// ordinal that becomes current, so a process that drives several GPUs sets every device up.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first();
+    void reset_current();            // setup failed: try again on the next call
+};
 int encode_tmap_bf16_2d(void *map, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }

@@ -56,6 +56,10 @@ struct Cfg {
     static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024;  // + 1024-byte alignment slack
 };
 
+// experiment switches (env SFB_GEMM_DBG, measurement aid only: results are wrong when set): 1 = no global stores in the epilogue,
+// 2 = every TMA load fetches tile (0, 0) (operands always L2-resident), 4 = no residual loads
+constexpr int DBG_NOSTORE = 1 << 16, DBG_SAMETILE = 1 << 17, DBG_NORES = 1 << 18;
+
 struct EpiParams {
     const float *bias;
     const float *residual;
@@ -191,6 +195,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 // its products only reach accumulator rows / columns that the epilogue masks
                 if (m0 >= p.M) m0 = 0;
                 if (n0 >= p.N) n0 = 0;
+                if (p.flags & DBG_SAMETILE) m0 = crank * BLOCK_M, n0 = rank * C::B_ROWS * (CG - 1);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = tiles_base + stage * STAGE_BYTES;
@@ -258,8 +263,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int q = warp & 3;               // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
         const int quarter = (warp - 2) >> 2;  // which 64 of the 256 accumulator columns
         const bool gelu = (p.flags & SFB_GEMM_GELU) != 0;
-        const bool has_res = (p.flags & SFB_GEMM_RESIDUAL) != 0;
+        const bool has_res = (p.flags & SFB_GEMM_RESIDUAL) != 0 && !(p.flags & DBG_NORES);
         const bool out_f32 = (p.flags & SFB_GEMM_OUT_F32) != 0;
+        const bool do_store = !(p.flags & DBG_NOSTORE);
         uint8_t *stage = smem_raw + (tiles_base - smem_u32(smem_raw)) + kStages * STAGE_BYTES + (warp - 2) * EPI_WARP_BYTES;
         uint8_t *st_row = stage + lane * 128;                 // this thread's accumulator row in the transpose buffer
         const int rr = lane >> 3, cc = lane & 7;              // read-back mapping: rows 4i + rr, 16-byte chunk cc
@@ -335,7 +341,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             float4 val = *reinterpret_cast<const float4 *>(stage + rloc * 128 + ((cc ^ (rloc & 7)) << 4));
                             if (grow < p.M && gcol < p.N) {
                                 if (has_res) val.x += res[i].x, val.y += res[i].y, val.z += res[i].z, val.w += res[i].w;
-                                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + grow * p.ldo + gcol) = val;
+                                if (do_store) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + grow * p.ldo + gcol) = val;
                             }
                         }
                         __syncwarp();
@@ -384,7 +390,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         const int rloc = 4 * i + rr;
                         const int64_t grow = m0 + rloc;
                         const uint4 val = *reinterpret_cast<const uint4 *>(stage + rloc * 128 + ((cc ^ (rloc & 7)) << 4));
-                        if (grow < p.M && gcol < p.N)
+                        if (grow < p.M && gcol < p.N && do_store)
                             *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + grow * p.ldo + gcol) = val;
                     }
                     __syncwarp();
@@ -488,6 +494,8 @@ extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const fl
     p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
     static const int order_env = getenv("SFB_GEMM_ORDER") ? atoi(getenv("SFB_GEMM_ORDER")) : 0;
     p.m_fastest = order_env;
+    static const int dbg_env = getenv("SFB_GEMM_DBG") ? atoi(getenv("SFB_GEMM_DBG")) : 0;
+    p.flags |= (dbg_env & 7) << 16;
 
     if (impl == 1) {
         dim3 grid((N + 63) / 64, (M + 63) / 64);
@@ -510,22 +518,19 @@ extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const fl
     if (rc != SFB_OK) return rc;
 
     if (cg == 1) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_once;
+        if (attr_once.first())
             SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
-            attr_set = true;
-        }
         const int num_tiles = p.num_m_blocks * p.num_n_blocks;
         const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
         gemm_bf16_tcgen05_kernel<1, 1><<<grid, kThreads, Cfg<1>::SMEM_BYTES, st>>>(tmap_a, tmap_w, p);
         SFB_CHECK_LAUNCH();
         return SFB_OK;
     }
-    static bool attr_set2 = false;
-    if (!attr_set2) {
+    static PerDeviceOnce attr_once2;
+    if (attr_once2.first()) {
         SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
         SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
-        attr_set2 = true;
     }
     p.num_m_blocks = (M + cl * BLOCK_M - 1) / (cl * BLOCK_M);           // 256-row (pair) or 512-row (two pairs) tiles
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;

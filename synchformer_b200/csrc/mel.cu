@@ -3,10 +3,14 @@
 //   dataset/transforms.py:826-834  log(x + 1e-6)
 //   dataset/transforms.py:836-858  pad time 65 -> 66 with 0.0 (log domain, before normalisation)
 //   dataset/transforms.py:861-871  (x - (-4.2677393)) / (2 * 4.5689974)
-// One CTA per (segment, STFT frame).  The periodic Hann(400) window sits at samples [312, 712) of the 1024-sample
-// frame, so only 400 products per bin are non-zero: a direct 400-term DFT for bins 0..512 with a 1024-entry
-// twiddle table in shared memory (bins k and 512-k computed together), accumulated in fp64 (a pure tone leaves most bins ~1e-8 of the peak, and
-// log(x + 1e-6) exposes fp32 summation error there).  |X|^2 is invariant to the 312-sample phase offset.
+// One CTA (256 threads) per (segment, STFT frame).  Only the 400 samples under the periodic Hann window are non-zero in the
+// 1024-sample frame, and |X|^2 does not depend on where they sit, so they are placed at positions 0..399.  The real 1024-point
+// transform is ONE 512-point complex FFT of z[n] = x[2n] + i x[2n+1] (radix-2 decimation in frequency in shared memory: 9 stages of 256
+// butterflies, natural-order input, bit-reversed output) followed by the even / odd split
+//     X[k] = E[k] + W^k O[k],   X[512 - k] = conj(E[k] - W^k O[k]),   E = (Z[k] + conj Z[512-k]) / 2,   O = (Z[k] - conj Z[512-k]) / 2i
+// - 2 304 butterflies per frame where the round-1 kernel spent 103 000 multiply-adds on a direct 400-term DFT per bin pair.
+// Everything up to |X|^2 stays in fp64: a pure tone leaves most bins ~1e-8 of the peak and log(x + 1e-6) exposes fp32 round-off there
+// (torchaudio's fp32 FFT sits 2.3e-4 from the fp64 oracle for that reason).
 // The 513 x 128 HTK triangle filterbank (L2-resident, 262 KB) is applied from shared-memory power values.
 #include <math.h>
 
@@ -23,41 +27,46 @@ __device__ double2 g_twiddle[N_FFT];       // (cos, sin)(2 pi j / 1024)
 __device__ float g_window[WIN];
 __device__ float g_fb[N_FREQ * N_MEL];     // [freq][mel]
 
-// X[k] and X[512 - k] share their twiddles: e^{-2 pi i (512-k) n / 1024} = (-1)^n e^{+2 pi i k n / 1024}.  With the sums over even
-// and odd n kept apart, one walk over the 400 windowed samples yields both bins: X[k] = (Ae + Ao) - i (Be + Bo),
-// X[512-k] = (Ae - Ao) + i (Be - Bo).  Threads 0..256 own the pairs (k, 512 - k).
-constexpr int MEL_THREADS = 288;
+constexpr int MEL_THREADS = 256;
+constexpr int N_HALF = N_FFT / 2;          // length of the complex transform
 
 __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float *__restrict__ wave, float *__restrict__ out, int n_segments,
                                                           int64_t clip_stride, int a_start, int a_stride) {
-    __shared__ double2 tw[N_FFT];
-    __shared__ float xs[WIN];
+    __shared__ double2 z[N_HALF];
     __shared__ float pw[N_FREQ + 3];
     const int frame = blockIdx.x % N_FRAMES;
     const int64_t seg = blockIdx.x / N_FRAMES;
     const int tid = threadIdx.x;
-    for (int j = tid; j < N_FFT; j += MEL_THREADS) tw[j] = g_twiddle[j];
     // segment `seg` = segment (seg % n_segments) of clip (seg / n_segments): windows may overlap inside one un-duplicated waveform
     const float *w = wave + (seg / n_segments) * clip_stride + a_start + (seg % n_segments) * static_cast<int64_t>(a_stride);
-    for (int n = tid; n < WIN; n += MEL_THREADS) {
+    auto sample = [&](int n) -> double {
         int idx = frame * HOP + WIN_OFF + n - N_FFT / 2;          // index into the un-padded segment
         idx = idx < 0 ? -idx : (idx >= SEG ? 2 * (SEG - 1) - idx : idx);   // reflect padding (torch.stft center=True)
-        xs[n] = __ldg(w + idx) * g_window[n];
-    }
+        return static_cast<double>(__ldg(w + idx) * g_window[n]);          // windowed in fp32, exactly like the oracle / torchaudio
+    };
+    for (int n = tid; n < N_HALF; n += MEL_THREADS) z[n] = 2 * n < WIN ? make_double2(sample(2 * n), sample(2 * n + 1)) : make_double2(0.0, 0.0);
     __syncthreads();
-    if (tid <= N_FFT / 4) {
-        const int k = tid;
-        double ae = 0.0, be = 0.0, ao = 0.0, bo = 0.0;
-#pragma unroll 4
-        for (int n = 0; n < WIN; n += 2) {
-            const double2 c0 = tw[(k * n) & (N_FFT - 1)], c1 = tw[(k * (n + 1)) & (N_FFT - 1)];
-            const double x0 = static_cast<double>(xs[n]), x1 = static_cast<double>(xs[n + 1]);
-            ae = fma(x0, c0.x, ae), be = fma(x0, c0.y, be);
-            ao = fma(x1, c1.x, ao), bo = fma(x1, c1.y, bo);
-        }
-        const double r0 = ae + ao, i0 = be + bo, r1 = ae - ao, i1 = be - bo;
+#pragma unroll 1
+    for (int half = N_HALF / 2; half >= 1; half >>= 1) {            // stage with butterflies of span `half`: one per thread
+        const int pos = tid & (half - 1);
+        const int i0 = ((tid - pos) << 1) + pos, i1 = i0 + half;
+        const double2 a = z[i0], b = z[i1];
+        const double2 t = g_twiddle[pos * (N_HALF / half)];          // (cos, sin)(2 pi pos / (2 half))
+        const double dr = a.x - b.x, di = a.y - b.y;
+        z[i0] = make_double2(a.x + b.x, a.y + b.y);
+        z[i1] = make_double2(fma(dr, t.x, di * t.y), fma(di, t.x, -dr * t.y));     // (dr + i di) e^{-i theta}
+        __syncthreads();
+    }
+    for (int k = tid; k <= N_HALF / 2; k += MEL_THREADS) {           // bin pairs (k, 512 - k); Z[k] sits at the bit-reversed index
+        const double2 zk = z[__brev(static_cast<unsigned>(k)) >> 23];
+        const double2 zm = z[__brev(static_cast<unsigned>((N_HALF - k) & (N_HALF - 1))) >> 23];
+        const double er = 0.5 * (zk.x + zm.x), ei = 0.5 * (zk.y - zm.y);          // E = (Z[k] + conj Z[512-k]) / 2
+        const double orr = 0.5 * (zk.y + zm.y), oi = -0.5 * (zk.x - zm.x);        // O = (Z[k] - conj Z[512-k]) / 2i
+        const double2 t = g_twiddle[k];                                           // W^k = cos - i sin
+        const double wr = fma(orr, t.x, oi * t.y), wi = fma(oi, t.x, -orr * t.y);
+        const double r0 = er + wr, i0 = ei + wi, r1 = er - wr, i1 = ei - wi;
         pw[k] = static_cast<float>(r0 * r0 + i0 * i0);
-        pw[N_FFT / 2 - k] = static_cast<float>(r1 * r1 + i1 * i1);   // k = 256 writes the same bin twice with the same value
+        if (k != N_HALF - k) pw[N_HALF - k] = static_cast<float>(r1 * r1 + i1 * i1);
     }
     __syncthreads();
     if (tid < N_MEL) {
@@ -70,8 +79,8 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float *__restric
 }
 
 static int init_tables() {
-    static bool done = false;
-    if (done) return SFB_OK;
+    static PerDeviceOnce once;            // the tables live in per-device global memory: upload them on every device that is used
+    if (!once.first()) return SFB_OK;
     static double2 tw[N_FFT];
     static float win[WIN];
     static float fb[N_FREQ * N_MEL];
@@ -98,7 +107,6 @@ static int init_tables() {
     SFB_CHECK_CUDA(cudaMemcpyToSymbol(g_twiddle, tw, sizeof(tw)));
     SFB_CHECK_CUDA(cudaMemcpyToSymbol(g_window, win, sizeof(win)));
     SFB_CHECK_CUDA(cudaMemcpyToSymbol(g_fb, fb, sizeof(fb)));
-    done = true;
     return SFB_OK;
 }
 

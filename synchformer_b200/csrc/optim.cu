@@ -25,38 +25,63 @@ struct TensorEntry {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// cross entropy: warp per row; row_loss[b] = logsumexp(logits[b]) - logits[b, target[b]];  dlogits = (softmax - onehot) / B
+// cross entropy: warp per row; row_loss[b] = logsumexp(logits[b]) - logits[b, target[b]];  dlogits = (softmax - onehot) / n_valid
+// Targets follow F.cross_entropy: -100 (its default ignore_index) drops the row from the loss, the gradient and the mean's denominator;
+// any other value outside [0, C) is an error - torch raises a device assert, here the loss and that row's gradient become NaN (loud,
+// without killing the context) and nothing is read out of bounds.
 // ---------------------------------------------------------------------------------------------------------------------------
+constexpr int64_t kIgnoreIndex = -100;
+
+__device__ __forceinline__ int count_valid_targets(const int64_t *__restrict__ targets, int B, int lane) {
+    int n = 0;
+    for (int b = lane; b < B; b += 32) n += targets[b] != kIgnoreIndex ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    return n;
+}
+
 __global__ void __launch_bounds__(256) cross_entropy_rows_kernel(const float *__restrict__ logits, const int64_t *__restrict__ targets, int B, int C,
                                                                  float *__restrict__ row_loss, float *__restrict__ dlogits) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
     if (b >= B) return;
+    const int n_valid = count_valid_targets(targets, B, lane);
     const float *row = logits + static_cast<int64_t>(b) * C;
+    const int64_t t64 = targets[b];
+    if (t64 == kIgnoreIndex) {
+        for (int c = lane; c < C; c += 32) dlogits[static_cast<int64_t>(b) * C + c] = 0.0f;
+        if (lane == 0) row_loss[b] = 0.0f;
+        return;
+    }
+    const bool bad = t64 < 0 || t64 >= C;
     float mx = -INFINITY;
     for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
     mx = warp_max(mx);
     float sum = 0.f;
     for (int c = lane; c < C; c += 32) sum += expf(row[c] - mx);
     sum = warp_sum(sum);
-    const int t = static_cast<int>(targets[b]);
-    const float inv = 1.0f / sum, invB = 1.0f / B;
-    for (int c = lane; c < C; c += 32) dlogits[static_cast<int64_t>(b) * C + c] = (expf(row[c] - mx) * inv - (c == t ? 1.0f : 0.0f)) * invB;
-    if (lane == 0) row_loss[b] = mx + logf(sum) - row[t];
+    const int t = bad ? 0 : static_cast<int>(t64);
+    const float inv = 1.0f / sum, invB = 1.0f / n_valid, poison = bad ? __uint_as_float(0x7fc00000u) : 0.0f;
+    for (int c = lane; c < C; c += 32) dlogits[static_cast<int64_t>(b) * C + c] = (expf(row[c] - mx) * inv - (c == t ? 1.0f : 0.0f)) * invB + poison;
+    if (lane == 0) row_loss[b] = mx + logf(sum) - row[t] + poison;
 }
 
-__global__ void __launch_bounds__(256) mean_kernel(const float *__restrict__ v, int n, float *__restrict__ out) {
+// out = sum(v) / (number of targets that are not ignore_index); all rows ignored -> NaN, as F.cross_entropy
+__global__ void __launch_bounds__(256) mean_kernel(const float *__restrict__ v, const int64_t *__restrict__ targets, int n, float *__restrict__ out) {
     __shared__ float red[8];
     float s = 0.f;
     for (int i = threadIdx.x; i < n; i += 256) s += v[i];
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
+    if (threadIdx.x < 32) {
+        const int n_valid = count_valid_targets(targets, n, threadIdx.x);
+        if (threadIdx.x == 0) {
+            float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k];
-        out[0] = t / n;
+            for (int k = 0; k < 8; ++k) t += red[k];
+            out[0] = t / n_valid;
+        }
     }
 }
 
@@ -153,7 +178,7 @@ extern "C" int sfb_cross_entropy(const float *logits, const int64_t *targets, in
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cross_entropy_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, targets, B, C, row_loss, dlogits);
     SFB_CHECK_LAUNCH();
-    mean_kernel<<<1, 256, 0, st>>>(row_loss, B, loss);
+    mean_kernel<<<1, 256, 0, st>>>(row_loss, targets, B, loss);
     SFB_CHECK_LAUNCH();
     return SFB_OK;
 }

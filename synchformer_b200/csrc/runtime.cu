@@ -17,15 +17,30 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
-    return n;
+static int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev & 63;
 }
+
+int num_sms() {
+    static int n[64] = {};
+    const int dev = current_device_slot();
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
+    }
+    return n[dev];
+}
+
+bool PerDeviceOnce::first() {
+    const int dev = current_device_slot();
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+void PerDeviceOnce::reset_current() { done[current_device_slot()] = false; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,

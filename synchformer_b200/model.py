@@ -16,6 +16,7 @@ differentiable (train.py), and so are the two feature extract
 """
 import logging
 import math
+import os
 from typing import Any, Dict, Mapping, Optional
 
 import torch
@@ -63,6 +64,35 @@ def _init_reference_like(module: nn.Module):
                 nn.init.trunc_normal_(p, std=0.02)
 
 
+def _init_from_stage1_ckpt(module: nn.Module, ckpt_path: str, encoder: str, what: str):
+    """Stage-I (AVCLIP) checkpoint -> feature-extractor initialisation, as motionformer.py:156-173 / ast.py:113-132 do when `ckpt_path`
+    ends with '.pt' (scripts/sbatch_train_sync.sh:74-75 launches stage II this way): keep the `[module.]{v,a}_encoder.` entries of
+    `ckpt['state_dict']`, strip the prefix, `load_state_dict(strict=False)`, and warn about missing / unexpected keys.
+    Other values of ckpt_path (the HF hub name of the AudioSet AST, the SSv2 `.pyth` Motionformer files) are public pre-trained
+    initialisations the reference downloads; there is no network here, so they are refused - load such weights with load_state_dict."""
+    if not str(ckpt_path).endswith('.pt'):
+        raise NotImplementedError(f"{what}: ckpt_path={ckpt_path!r} is a downloadable pre-trained initialisation (harness work, needs the network); "
+                                  "only stage-I '.pt' checkpoints are initialised from here - load other weights with load_state_dict")
+    if not os.path.exists(ckpt_path):
+        raise ValueError(f'Cant find the checkpoint file: {ckpt_path}.', 'Please download it manually and ensure the path exists.')   # utils/utils.py:57-58
+    try:
+        ckpt = torch.load(ckpt_path, map_location='cpu', weights_only=True)
+    except Exception:                                   # reference checkpoints also pickle their OmegaConf `args`
+        ckpt = torch.load(ckpt_path, map_location='cpu', weights_only=False)
+    weights = {}
+    for k, v in ckpt['state_dict'].items():
+        if k.startswith((f'module.{encoder}.', f'{encoder}.')):
+            weights[k.replace('module.', '').replace(f'{encoder}.', '')] = v
+    status = module.load_state_dict(weights, strict=False)
+    if len(status.missing_keys) > 0 or len(status.unexpected_keys) > 0:
+        logging.warning(f'Loading exact {what} ckpt from {ckpt_path} failed. \nMissing keys ({len(status.missing_keys)}): {status.missing_keys}, \n'
+                        f'Unexpected keys ({len(status.unexpected_keys)}): {status.unexpected_keys} \n'
+                        'temp_attn_agg are expected to be missing if ckpt was pt contrastively.')
+    else:
+        logging.info(f'Loading {what} ckpt from {ckpt_path} succeeded.')
+    return status
+
+
 def _tower_trains(m: nn.Module) -> bool:
     """A feature extractor takes the differentiable path iff it is in train mode, autograd is on and it has trainable parameters
     (stage I, or stage II with `is_trainable: True`); frozen / eval towers keep the inference path."""
@@ -76,6 +106,14 @@ class _KernelModule(nn.Module):
         super().__init__()
         self._wcache: Dict[str, torch.Tensor] = {}
         self._wcache_key = None
+        self._taps: Optional[Dict[str, torch.Tensor]] = None     # parity tests set a dict here to receive copies of the residual stream
+
+    def _tap(self, name: str, x: torch.Tensor, rows_per_item: int):
+        """Diagnostic tap (tests only; None on the product path): fp32 copy of `x` viewed as (items, rows_per_item, 768), under the names
+        tests/golden/make_golden.py and the oracle use."""
+        if self._taps is not None:
+            t = x.detach().float().clone().view(-1, rows_per_item, D)
+            self._taps[name] = torch.cat([self._taps[name], t], dim=0) if name in self._taps else t
 
     def _own_params(self) -> Dict[str, nn.Parameter]:
         return dict(self.named_parameters())
@@ -146,8 +184,7 @@ class MotionFormer(_KernelModule):
         if not extract_features or not factorize_space_time or agg_space_module != 'TransformerEncoderLayer' or add_global_repr:
             raise NotImplementedError('synchformer_b200.MotionFormer supports extract_features=True, factorize_space_time=True, '
                                       "agg_space_module='TransformerEncoderLayer', add_global_repr=False (configs/sync.yaml:18-27)")
-        if ckpt_path is not None:
-            raise NotImplementedError('ckpt_path download/initialisation is harness work; load weights with load_state_dict')
+        self.ckpt_path = ckpt_path
         self.time_pool = 'AveragePooling' in str(agg_time_module)
         if not self.time_pool and 'Identity' not in str(agg_time_module):
             raise NotImplementedError(f'agg_time_module={agg_time_module}')
@@ -157,6 +194,8 @@ class MotionFormer(_KernelModule):
         schema = {k[len('vfeat_extractor.'):]: v for k, v in state_dict_schema().items() if k.startswith('vfeat_extractor.')}
         _build_tree(self, schema)
         _init_reference_like(self)
+        if ckpt_path is not None:
+            _init_from_stage1_ckpt(self, ckpt_path, 'v_encoder', 'vfeat_extractor')
         self.patch_embed.requires_grad_(False)                       # motionformer.py:177
 
     def _pack(self, P):
@@ -196,6 +235,7 @@ class MotionFormer(_KernelModule):
         patch = ops.gemm(a, W['pe_w'], P['patch_embed_3d.proj.bias'], out_f32=True)
         x = ops.video_tokens(patch, P['cls_token'], P['pos_embed'], P['temp_embed'], n)           # (n*1569, 768) fp32 residual stream
         del a, patch
+        self._tap('v_embed', x, V_TOK)
         M = n * V_TOK
         ln = torch.empty((M, D), device=dev, dtype=torch.bfloat16)
         qkv = torch.empty((M, 3 * D), device=dev, dtype=torch.bfloat16)
@@ -214,6 +254,8 @@ class MotionFormer(_KernelModule):
             ops.layernorm(x, P[b + 'norm2.weight'], P[b + 'norm2.bias'], EPS_V, out=ln)
             ops.gemm(ln, W[b + 'mlp.fc1'], P[b + 'mlp.fc1.bias'], out=hid, gelu=True)
             ops.gemm(hid, W[b + 'mlp.fc2'], P[b + 'mlp.fc2.bias'], out=x, residual=x, out_f32=True)
+            if i in (0, 11):
+                self._tap(f'v_block{i}', x, V_TOK)
         # final norm on the 1568 non-CLS tokens (motionformer.py:229-232) fused with the aggregator's norm1
         g = 'spatial_attn_agg.'
         kv_src = ops.layernorm(x, P['norm.weight'], P['norm.bias'], EPS_V, out=ln[:n * 1568], rows=n * 1568, group=1568, group_stride=V_TOK,
@@ -267,8 +309,7 @@ class AST(_KernelModule):
         if not extract_features or not factorize_freq_time or agg_freq_module != 'TransformerEncoderLayer' or add_global_repr:
             raise NotImplementedError('synchformer_b200.AST supports extract_features=True, factorize_freq_time=True, '
                                       "agg_freq_module='TransformerEncoderLayer', add_global_repr=False (configs/sync.yaml:6-17)")
-        if ckpt_path is not None:
-            raise NotImplementedError('ckpt_path download/initialisation is harness work; load weights with load_state_dict')
+        self.ckpt_path = ckpt_path
         if max_spec_t not in (None, 66):
             raise NotImplementedError('max_spec_t must be 66 (74 position embeddings)')
         self.time_pool = 'AveragePooling' in str(agg_time_module)
@@ -278,6 +319,8 @@ class AST(_KernelModule):
         schema = {k[len('afeat_extractor.'):]: v for k, v in state_dict_schema().items() if k.startswith('afeat_extractor.')}
         _build_tree(self, schema)
         _init_reference_like(self)
+        if ckpt_path is not None:
+            _init_from_stage1_ckpt(self, ckpt_path, 'a_encoder', 'afeat_extractor')
 
     def _pack(self, P):
         W = {'pe_w': self._bf16(P['ast.embeddings.patch_embeddings.projection.weight'])}
@@ -313,6 +356,7 @@ class AST(_KernelModule):
         a = ops.im2col_ast(spec.float().contiguous().view(n, 128, 66))
         patch = ops.gemm(a, W['pe_w'], P[e + 'patch_embeddings.projection.bias'], out_f32=True)
         x = ops.ast_tokens(patch, P[e + 'cls_token'], P[e + 'distillation_token'], P[e + 'position_embeddings'], n)   # (n*74, 768) fp32
+        self._tap('a_embed', x, A_TOK)
         M = n * A_TOK
         dev = x.device
         ln = torch.empty((M, D), device=dev, dtype=torch.bfloat16)
@@ -333,6 +377,8 @@ class AST(_KernelModule):
         # final layernorm (modeling_ast.py:543) on the 72 patch tokens (ast.py:232-233) fused with the aggregator's norm1;
         # rows stay in (seg, f, t) order and the aggregator walks them with stride 6 (ast.py:266-268 without the permute copy)
         g = 'freq_attn_agg.'
+        if self._taps is not None:          # the product path never materialises the un-gathered final norm; the tap computes it on the side
+            self._tap('a_last_hidden', ops.layernorm(x, P['ast.layernorm.weight'], P['ast.layernorm.bias'], EPS_A, out_f32=True), A_TOK)
         kv_src = ops.layernorm(x, P['ast.layernorm.weight'], P['ast.layernorm.bias'], EPS_A, out=ln[:n * 72], rows=n * 72, group=72,
                                group_stride=A_TOK, offset=2, gamma2=P[g + 'norm1.weight'], beta2=P[g + 'norm1.bias'], eps2=EPS_V)
         feats = _cls_aggregator(P, W, g, kv_src, n, A_T, 72, 1, A_T, A_F).view(B, S, A_T, D)
@@ -476,16 +522,20 @@ class Synchformer(nn.Module):
             self._proj_key = key
         return self._proj_cache
 
-    def project(self, vis: torch.Tensor, aud: torch.Tensor):
-        """vproj / aproj (sync_model.py:55-56) + segment flattening (:59-62).  (B,S,8,768),(B,S,6,768) -> (B,8S,768),(B,6S,768) fp32."""
+    def project(self, vis: torch.Tensor, aud: torch.Tensor, out_v: Optional[torch.Tensor] = None, out_a: Optional[torch.Tensor] = None):
+        """vproj / aproj (sync_model.py:55-56) + segment flattening (:59-62).  (B,S,8,768),(B,S,6,768) -> (B,8S,768),(B,6S,768) fp32.
+        out_v (B*S*8, 768) / out_a (B*S*6, 768) fp32: inference only - the GEMM epilogues write there (parallel.py passes slices of the
+        all-gather send buffer, so no copy sits between the projection and the collective)."""
         B, S = vis.shape[:2]
         Wp = self._proj_weights()
         if self.training:
+            if out_v is not None or out_a is not None:
+                raise NotImplementedError('project(out_v=, out_a=) is an inference-path option')
             v = train.linear(vis.float().contiguous().view(-1, D), self.vproj.weight, self.vproj.bias, Wp['v'])        # N3: differentiable
             a = train.linear(aud.float().contiguous().view(-1, D), self.aproj.weight, self.aproj.bias, Wp['a'])
             return v.view(B, S * 8, D), a.view(B, S * 6, D)
-        v = ops.gemm(ops.cast_bf16(vis.float().contiguous().view(-1, D)), Wp['v'], self.vproj.bias.detach(), out_f32=True)
-        a = ops.gemm(ops.cast_bf16(aud.float().contiguous().view(-1, D)), Wp['a'], self.aproj.bias.detach(), out_f32=True)
+        v = ops.gemm(ops.cast_bf16(vis.float().contiguous().view(-1, D)), Wp['v'], self.vproj.bias.detach(), out=out_v, out_f32=True)
+        a = ops.gemm(ops.cast_bf16(aud.float().contiguous().view(-1, D)), Wp['a'], self.aproj.bias.detach(), out=out_a, out_f32=True)
         return v.view(B, S * 8, D), a.view(B, S * 6, D)
 
     # ---- reference API -------------------------------------------------------------------------------------------

@@ -27,6 +27,11 @@ def launch_count() -> int:
 
 
 def _stream(t: torch.Tensor):
+    """Current stream of the tensor's device.  Kernels launch on the CURRENT device, so the tensor must live there: a model on cuda:1
+    without `torch.cuda.set_device(1)` / `with torch.cuda.device(1)` is refused instead of launching with a foreign stream handle."""
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise _lib.SfbError(f'tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: '
+                            'select the device first (torch.cuda.set_device / torch.cuda.device)')
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
@@ -474,3 +479,88 @@ def gather_rows_bf16(x: torch.Tensor, rows: int, group: Optional[int] = None, gr
     check(_lib.load().sfb_gather_rows_bf16(_p(x), x.stride(0), _p(out), rows, group, group_stride, offset, _stream(x)), 'sfb_gather_rows_bf16')
     _count()
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N1: tail of the stage-I contrastive step (see include/synchformer_b200.h, "contrastive")
+# ------------------------------------------------------------------------------------------------------------------
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    require_cuda(t, name)
+    assert t.dtype == torch.float32 and t.is_contiguous(), f'{name} must be contiguous fp32'
+    return t
+
+
+def mean_tokens(x: torch.Tensor) -> torch.Tensor:
+    """(n, T, D) fp32 -> (n, D): AveragePooling over the token rows (motionformer.py:405-409)."""
+    _f32c(x, 'x')
+    n, T, Dm = x.shape
+    out = torch.empty((n, Dm), device=x.device, dtype=torch.float32)
+    check(_lib.load().sfb_mean_tokens(_p(x), _p(out), n, T, Dm, _stream(x)), 'sfb_mean_tokens')
+    _count()
+    return out
+
+
+def mean_tokens_bwd(dout: torch.Tensor, T: int) -> torch.Tensor:
+    _f32c(dout, 'dout')
+    n, Dm = dout.shape
+    dx = torch.empty((n, T, Dm), device=dout.device, dtype=torch.float32)
+    check(_lib.load().sfb_mean_tokens_bwd(_p(dout), _p(dx), n, T, Dm, _stream(dout)), 'sfb_mean_tokens_bwd')
+    _count()
+    return dx
+
+
+def l2_normalize(x: torch.Tensor):
+    """F.normalize(x, dim=-1) on (n, D) fp32 -> (xn, inv_norm (n,))."""
+    _f32c(x, 'x')
+    n, Dm = x.shape
+    xn = torch.empty_like(x)
+    inv = torch.empty((n,), device=x.device, dtype=torch.float32)
+    check(_lib.load().sfb_l2_normalize(_p(x), _p(xn), _p(inv), n, Dm, _stream(x)), 'sfb_l2_normalize')
+    _count()
+    return xn, inv
+
+
+def l2_normalize_bwd(xn: torch.Tensor, inv_norm: torch.Tensor, dxn: torch.Tensor) -> torch.Tensor:
+    _f32c(xn, 'xn'), _f32c(inv_norm, 'inv_norm'), _f32c(dxn, 'dxn')
+    n, Dm = xn.shape
+    dx = torch.empty_like(xn)
+    check(_lib.load().sfb_l2_normalize_bwd(_p(xn), _p(inv_norm), _p(dxn), _p(dx), n, Dm, _stream(xn)), 'sfb_l2_normalize_bwd')
+    _count()
+    return dx
+
+
+def contrastive_loss(vn: torch.Tensor, an: torch.Tensor, vn_all: torch.Tensor, an_all: torch.Tensor, scale: torch.Tensor):
+    """open_clip/model.py:507-527 on normalised features: local rows (n, D) as queries, gathered rows (N, D) as keys; scale: the 1-element
+    fp32 device tensor holding logit_scale (read on the device).  -> (loss (1,), dscale (1,), G (2, n, N)) device tensors."""
+    for t, nm in ((vn, 'vn'), (an, 'an'), (vn_all, 'vn_all'), (an_all, 'an_all'), (scale, 'scale')):
+        _f32c(t, nm)
+    n, Dm = vn.shape
+    N = vn_all.shape[0]
+    assert an.shape == (n, Dm) and vn_all.shape == (N, Dm) and an_all.shape == (N, Dm) and scale.numel() == 1
+    dev = vn.device
+    loss, dscale = torch.empty((1,), device=dev, dtype=torch.float32), torch.empty((1,), device=dev, dtype=torch.float32)
+    G = torch.empty((2, n, N), device=dev, dtype=torch.float32)
+    ws = torch.empty((4 * n,), device=dev, dtype=torch.float32)
+    check(_lib.load().sfb_contrastive_loss(_p(vn), _p(an), _p(vn_all), _p(an_all), n, N, Dm, _p(scale), _p(loss), _p(dscale), _p(G), _p(ws), _stream(vn)),
+          'sfb_contrastive_loss')
+    _count(2)
+    return loss, dscale, G
+
+
+def contrastive_loss_bwd(vn: torch.Tensor, an: torch.Tensor, vn_all: Optional[torch.Tensor], an_all: Optional[torch.Tensor], G: torch.Tensor,
+                         scale: torch.Tensor, upstream: torch.Tensor, dscale: torch.Tensor):
+    """-> (d_vn, d_an (n, D), d_vn_all, d_an_all (N, D) or None, dscale_out (1,)), all times the device scalar `upstream`.
+    vn_all / an_all None: the keys are the local rows themselves (no gathering) and their gradient is folded into d_vn / d_an."""
+    n, Dm = vn.shape
+    local = vn_all is None
+    kv, ka = (vn, an) if local else (vn_all, an_all)
+    N = kv.shape[0]
+    for t, nm in ((G, 'G'), (scale, 'scale'), (upstream, 'upstream'), (dscale, 'dscale')):
+        _f32c(t, nm)
+    d_vn, d_an = torch.empty_like(vn), torch.empty_like(an)
+    d_vn_all, d_an_all = (None, None) if local else (torch.empty_like(kv), torch.empty_like(ka))
+    dscale_out = torch.empty((1,), device=vn.device, dtype=torch.float32)
+    check(_lib.load().sfb_contrastive_loss_bwd(_p(vn), _p(an), _p(kv), _p(ka), _p(G), n, N, Dm, _p(scale), _p(upstream), _p(dscale), _p(d_vn), _p(d_an),
+                                               _p(d_vn_all), _p(d_an_all), _p(dscale_out), _stream(vn)), 'sfb_contrastive_loss_bwd')
+    _count(2)
+    return d_vn, d_an, d_vn_all, d_an_all, dscale_out

@@ -11,8 +11,9 @@ the skip-step-on-inf/nan rule - all driven by a device-side gradient norm, so th
     # drop-in use (the harness keeps its GradScaler / clip_grad_norm_ calls):   scaler.step(opt)  or  opt.step()
     # fused use (replaces unscale_ + clip_grad_norm_ + step):                   norm, found_inf = opt.step(grad_scale=s, max_norm=1.0)
 
-Parameters and gradients must be contiguous fp32 CUDA tensors.  State (`exp_avg`, `exp_avg_sq` per parameter, one device-side step counter)
-is created lazily.  No CPU path.
+Parameters and gradients must be contiguous fp32 CUDA tensors.  State (`exp_avg`, `exp_avg_sq`, `step` per parameter as in
+torch.optim.Adam - the step counter is one device tensor shared by a group) is created lazily and round-trips through `state_dict()`; every
+step bumps the parameters' version counters so the bf16 weight caches of model.py are rebuilt.  No CPU path.
 """
 import ctypes
 from typing import Optional
@@ -56,13 +57,47 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self._dev_state = {}
 
-    def _group_state(self, gi: int, device):
+    def _group_state(self, gi: int, device, ps):
+        """Device-side scalars of one parameter group.  The completed-step counter lives in `self.state[p]['step']` (ONE 0-dim fp32 device
+        tensor shared by all parameters of the group), so it round-trips through `state_dict()` / `load_state_dict()` exactly like
+        torch.optim.Adam's per-parameter `step` - the reference logger checkpoints and restores the optimiser (utils/logger.py:146-151)."""
         st = self._dev_state.get(gi)
-        if st is None or st['step'].device != device:
-            st = dict(step=torch.zeros((1,), device=device, dtype=torch.float32), sqnorm=torch.zeros((1,), device=device, dtype=torch.float32),
+        if st is None or st['sqnorm'].device != device:
+            st = dict(step=None, sqnorm=torch.zeros((1,), device=device, dtype=torch.float32),
                       found_inf=torch.zeros((1,), device=device, dtype=torch.float32))
             self._dev_state[gi] = st
+        shared = st['step']
+        if shared is None or any(self.state[p].get('step') is not shared for p in ps):
+            # first step, new parameters, or a state restored by load_state_dict (possibly torch.optim.Adam's: one tensor per parameter,
+            # possibly on the CPU): adopt the largest restored count (they are equal in any state this class or Adam wrote)
+            seen = [float(self.state[p]['step']) for p in ps if torch.is_tensor(self.state[p].get('step')) or isinstance(self.state[p].get('step'), (int, float))]
+            if shared is not None:
+                seen.append(float(shared))
+            shared = torch.full((), max(seen) if seen else 0.0, device=device, dtype=torch.float32)
+            for p in ps:
+                self.state[p]['step'] = shared
+            st['step'] = shared
         return st
+
+    def state_dict(self):
+        """torch.optim.Optimizer.state_dict with one `step` tensor PER parameter (copies of the group's shared counter), which is the
+        layout torch.optim.Adam writes and expects - it increments every parameter's `step` separately."""
+        sd = super().state_dict()
+        sd['state'] = {k: ({**v, 'step': v['step'].detach().clone()} if torch.is_tensor(v.get('step')) else dict(v)) for k, v in sd['state'].items()}
+        return sd
+
+    @staticmethod
+    def _bump_versions(ps):
+        """The kernel writes through raw pointers, which torch's version counters do not see; everything keyed on `p._version` (the bf16
+        GEMM-weight caches of model.py, autograd's saved-tensor checks) must observe the update."""
+        setter = getattr(torch._C._autograd, '_unsafe_set_version_counter', None)
+        if setter is not None:
+            try:
+                setter(tuple(ps), tuple(p._version + 1 for p in ps))
+                return
+            except TypeError:
+                pass
+        torch._foreach_add_(list(ps), 0.0)            # no-op in value, bumps every version counter
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: Optional[float] = None, max_norm: Optional[float] = None):
@@ -88,8 +123,11 @@ class FusedAdam(torch.optim.Optimizer):
                 if not g.is_contiguous():
                     p.grad = g = g.contiguous()
                 st = self.state[p]
-                if not st:
+                if 'exp_avg' not in st:
                     st['exp_avg'], st['exp_avg_sq'] = torch.zeros_like(p), torch.zeros_like(p)
+                for k_ in ('exp_avg', 'exp_avg_sq'):          # restored states may sit on another device / dtype
+                    if st[k_].device != p.device or st[k_].dtype != torch.float32 or not st[k_].is_contiguous():
+                        st[k_] = st[k_].to(device=p.device, dtype=torch.float32).contiguous()
                 n = p.numel()
                 rows.append([p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(), n])
                 for s in range(0, n, chunk):
@@ -99,7 +137,7 @@ class FusedAdam(torch.optim.Optimizer):
             ct = torch.tensor(chunk_tensor, dtype=torch.int32).to(dev)
             cs = torch.tensor(chunk_start, dtype=torch.int64).to(dev)
             n_chunks = len(chunk_tensor)
-            gs = self._group_state(gi, dev)
+            gs = self._group_state(gi, dev, ps)
             stream = ops._stream(ps[0])
             fused = grad_scale is not None or max_norm is not None
             if fused:
@@ -114,6 +152,7 @@ class FusedAdam(torch.optim.Optimizer):
                                     float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']), inv_scale,
                                     float(max_norm) if max_norm is not None else 0.0, stream), 'sfb_adam_step')
             ops._count(2)
+            self._bump_versions(ps)
             if fused:
                 ret = (gs['sqnorm'].sqrt() * inv_scale, gs['found_inf'])
         return ret

@@ -16,7 +16,7 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(REPO, 'synchformer_b200', 'csrc')
 OUT = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT, 'libsfb_emu.so')
-SOURCES = ['train.cu', 'attention_train.cu', 'attention_bwd.cu', 'optim.cu',
+SOURCES = ['train.cu', 'attention_train.cu', 'attention_bwd.cu', 'optim.cu', 'contrastive.cu',
            # kernels that were verified on the B200 in round 1 and contain no inline PTX: running them here validates the emulator itself
            'layernorm.cu', 'embed.cu', 'attention.cu']
 CUDA_INC = os.environ.get('CUDA_INC', '/usr/local/cuda/include')

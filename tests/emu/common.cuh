@@ -390,6 +390,11 @@ inline void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 inline int num_sms() { return 148; }
+struct PerDeviceOnce {          // one emulated device
+    bool done = false;
+    bool first() { bool f = !done; done = true; return f; }
+    void reset_current() { done = false; }
+};
 
 #define SFB_CHECK_ARG(cond, ...)          \
     do {                                  \

@@ -64,6 +64,73 @@ def test_forward_matches_reference_golden(model_s2, golden):
     assert rel_l2(vf[0], vf[1]) > 5e-2
 
 
+TAP_TOL = 1e-2        # same gate as the segment features: rel-L2 of the fp32 residual stream against the fp32 reference / oracle
+
+
+def _with_taps(model, fn):
+    taps_v, taps_a = {}, {}
+    model.vfeat_extractor._taps, model.afeat_extractor._taps = taps_v, taps_a
+    try:
+        with torch.no_grad():
+            out = fn()
+    finally:
+        model.vfeat_extractor._taps, model.afeat_extractor._taps = None, None
+    return out, {**taps_v, **taps_a}
+
+
+def test_intermediate_taps_match_reference_golden(model_s2, golden):
+    """Where does the logits error come from?  The golden file holds strided samples of the reference's fp32 residual stream after the
+    patch embedding, after block 0 and block 11 of the Motionformer, and at both ends of the AST; every stage is gated on its own, and
+    the per-stage table is printed (DESIGN.md section 5 quotes it)."""
+    from synchformer_b200 import synth
+    g, aud = golden
+    st_tok, st_d = int(g['meta'][4]), int(g['meta'][5])
+    vis = synth.synthetic_video(2, 2, 0)
+    (_, logits), taps = _with_taps(model_s2, lambda: model_s2(vis.cuda(), aud.cuda()))
+    torch.cuda.synchronize()
+    rows = []
+    for name in ('v_embed', 'v_block0', 'v_block11', 'a_embed', 'a_last_hidden'):
+        got = taps[name][:, ::st_tok, ::st_d].cpu()
+        assert got.shape == g[name].shape, (name, got.shape, g[name].shape)
+        rows.append((name, rel_l2(got, g[name]), float((got - torch.from_numpy(g[name])).abs().max())))
+    print('per-stage error vs reference fp32 golden (rel-L2, max-abs): ' + '; '.join('%s %.2e %.2e' % r for r in rows))
+    for name, rel, _ in rows:
+        assert rel <= TAP_TOL, (name, rel)
+    assert dict((r[0], r[1]) for r in rows)['v_embed'] < 3e-3         # one bf16 GEMM away from the input
+    assert model_s2.vfeat_extractor._taps is None
+
+
+def test_config2_shape_single_clip_matches_oracle(cuda_device):
+    """BASELINE.json config 2's own shape (S = 8 segments, block_shape [114], fp16 video) for ONE clip against the fp32 CPU oracle, with the
+    per-stage error table: patch embedding -> block 0 -> block 11 -> segment features -> logits.  (The B = 64 batch of config 2 is
+    covered by bit-exact batch invariance below: every clip's logits equal the logits of the same clip run alone.)"""
+    from oracle import synchformer_oracle as O
+    from synchformer_b200 import model as M, ops, synth
+    B, S = 1, 8
+    sd = synth.synthetic_state_dict(1337, n_segments=S)
+    model = M.build_synchformer(n_segments=S, state_dict=sd, device=cuda_device)
+    assert model.transformer.pos_emb_cfg.pos_emb.shape[1] == 114
+    vis = synth.synthetic_video(B, S, seed=7).half()
+    wave = synth.synthetic_waveform(B, S, seed=7)
+
+    def run():
+        mel = ops.mel_frontend(wave.cuda()).unsqueeze(2)
+        return model(vis.cuda(), mel), model.extract_vfeats(vis.cuda()), model.extract_afeats(mel)
+    ((_, logits), vf, af), taps = _with_taps(model, run)
+    ref_taps = {}
+    _, ref = O.forward(sd, vis.float(), O.mel_frontend(wave).float().unsqueeze(2), taps=ref_taps)
+    n = B * S
+    rows = [(k, rel_l2(taps[k][:n], ref_taps[k])) for k in ('v_embed', 'v_block0', 'v_block11', 'a_embed', 'a_last_hidden')]
+    rows += [('vfeats', rel_l2(vf, ref_taps['vfeats'])), ('afeats', rel_l2(af, ref_taps['afeats'])), ('logits', rel_l2(logits, ref))]
+    print('config-2 shape (B=1, S=8) per-stage rel-L2 vs fp32 oracle: ' + '; '.join('%s %.2e' % r for r in rows)
+          + '; logits max-abs %.2e' % float((logits.cpu() - ref).abs().max()))
+    for name, rel in rows[:-1]:
+        assert rel <= TAP_TOL, (name, rel)
+    assert (logits.cpu() - ref).abs().max() <= LOGIT_ABS
+    assert rel_l2(logits, ref) <= LOGIT_REL
+    assert torch.equal(logits.argmax(-1).cpu(), ref.argmax(-1))
+
+
 @pytest.mark.parametrize('video_dtype', [torch.float16, torch.uint8])
 def test_forward_matches_oracle_on_fresh_inputs(cuda_device, video_dtype):
     """New weights / inputs (not the golden ones), fp16 video as RGBToHalfToZeroOne delivers it and raw uint8 frames (N2),

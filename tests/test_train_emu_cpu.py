@@ -116,6 +116,7 @@ def test_no_out_of_bounds_access_under_guard_pages():
 
 
 test_fused_cross_entropy_and_adam = G.test_fused_cross_entropy_and_adam
+test_fused_adam_updates_reach_the_model_forward = G.test_fused_adam_updates_reach_the_model_forward
 
 
 def test_emulator_reproduces_kernels_that_are_verified_on_hardware(monkeypatch):

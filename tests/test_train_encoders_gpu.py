@@ -2,9 +2,8 @@
 (forward with DropPath + hand-written backward, 448 gradient tensors) against torch autograd on the fp32 CPU oracle with the same DropPath
 multipliers, the AVCLIP step and stage II with trainable extractors end to end.
 
-STATUS: written after this round's GPU budget was spent.  The same kernel sources pass these checks on the CPU SIMT emulator
-(tests/test_train_encoders_cpu.py, tests/emu/), but they have not yet run on hardware, hence xfail(strict=False): they RUN on the GPU box,
-a pass shows as XPASS, a failure does not mask the verified inference suite.  Remove the marker once they have been seen green.
+The same kernel sources also pass these checks on the CPU SIMT emulator (tests/test_train_encoders_cpu.py, tests/emu/).  These tests gate:
+they were seen green on a B200 (GPUTEST_r01) and carry no xfail marker.
 """
 import os
 
@@ -18,8 +17,7 @@ from synchformer_b200 import avclip, model as M, ops, synth, train_encoders as T
 
 import test_train_encoders_cpu as C
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='N1 kernels not yet run on hardware (GPU budget of the round was spent before they were written)')]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(autouse=True)

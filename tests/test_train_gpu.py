@@ -2,10 +2,9 @@
 its contract (tests/fake_ops.py, oracle/philox.py), and the whole step (forward with dropout, backward, 63 gradient tensors) against
 torch autograd on the fp32 oracle with the same dropout multipliers.
 
-STATUS: these kernels were written after this round's GPU budget was spent, so they have compiled for sm_100a but have not yet run on
-hardware.  The tests are therefore marked xfail(strict=False): they RUN on the GPU box, a pass shows up as XPASS, a failure does not
-mask the verified inference suite.  Remove the marker once they have been seen green.
+These tests gate: they were seen green on a B200 (GPUTEST_r01: 42 / 42 of the training tests passed) and carry no xfail marker.
 """
+import copy
 import math
 import os
 
@@ -21,8 +20,7 @@ from synchformer_b200 import model as M, ops, synth, train
 import fake_ops
 import train_gates
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='N3 kernels not yet run on hardware (GPU budget of the round was spent before they were written)')]
+pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 D = 768
@@ -355,6 +353,80 @@ def test_fused_cross_entropy_and_adam(cuda_device):
     norm, found = a.step(grad_scale=1.0, max_norm=1.0)
     assert float(found) == 1.0 and all(torch.equal(p, q) for p, q in zip(mine, before))
     assert float(a._dev_state[0]['step']) == 4.0
+    # every real step bumps the parameters' version counters (the bf16 weight caches of model.py are keyed on them)
+    assert all(p._version >= 4 for p in mine)
+    # the step counter round-trips through state_dict(), in both directions between FusedAdam and torch.optim.Adam (resume from a checkpoint
+    # that either optimiser wrote): one more step after the reload must match the uninterrupted torch.optim.Adam run
+    assert all(float(a.state[p]['step']) == 4.0 for p in mine)
+    grads = [torch.randn(s, generator=gen) * 0.1 for s in shapes]
+    resumed = {}
+    for name, src in (('fused->fused', a), ('adam->fused', b)):
+        ps = [torch.nn.Parameter(q.detach().clone()) for q in theirs]
+        opt = optim.FusedAdam(ps, lr=1e-2, betas=(0.9, 0.999), eps=1e-7, weight_decay=0.01)
+        opt.load_state_dict(copy.deepcopy(src.state_dict()))      # load_state_dict aliases tensors that already have the right dtype / device
+        for p, gr in zip(ps, grads):
+            p.grad = gr.clone().to(dev)
+        opt.step()
+        assert float(opt.state[ps[0]]['step']) == 5.0, name
+        resumed[name] = ps
+    ps = [torch.nn.Parameter(q.detach().clone()) for q in theirs]
+    opt = torch.optim.Adam(ps, lr=1e-2, betas=(0.9, 0.999), eps=1e-7, weight_decay=0.01)
+    opt.load_state_dict(copy.deepcopy(a.state_dict()))               # fused -> torch.optim.Adam
+    for p, q, gr in zip(ps, theirs, grads):
+        p.grad, q.grad = gr.clone().to(dev), gr.clone().to(dev)
+    opt.step()
+    b.step()
+    for name, got in list(resumed.items()) + [('fused->adam', ps)]:
+        for p, q in zip(got, theirs):
+            assert (p - q).abs().max() < 2e-6, name
+    # F.cross_entropy target conventions: -100 rows are ignored (loss, gradient, denominator); other out-of-range targets poison the loss
+    t2 = targets.clone()
+    t2[::5] = -100
+    lg2 = logits.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        loss = optim.cross_entropy(lg2, t2)
+        (g,) = torch.autograd.grad(loss, lg2)
+        ref = torch.nn.functional.cross_entropy(lg2, t2)
+        (rg,) = torch.autograd.grad(ref, lg2)
+    assert abs(float(loss) - float(ref)) < 1e-6 and (g - rg).abs().max() < 1e-6 and float(g[0].abs().max()) == 0.0
+    t2[1] = 21
+    assert torch.isnan(optim.cross_entropy(logits.detach(), t2))
+
+
+def test_fused_adam_updates_reach_the_model_forward(cuda_device, monkeypatch):
+    """FusedAdam writes parameters through raw pointers; the bf16 GEMM-weight caches are keyed on the parameters' version
+    counters, so every step must bump them.  Three training steps of the synchronisation module with FusedAdam must track the same steps
+    with torch.optim.Adam: same losses / logits to bf16 noise, and the logits must MOVE between steps (a stale cache would freeze the GEMM weights)."""
+    from synchformer_b200 import optim
+    B, S = 2, 2
+    torch.manual_seed(11)
+    sd = synth.synthetic_state_dict(1337, n_segments=S)
+    vf, af = (torch.randn((B, S, 8, D)) * 0.5).to(cuda_device), (torch.randn((B, S, 6, D)) * 0.5).to(cuda_device)
+    targets = torch.tensor([3, 17]).to(cuda_device)
+    runs = {}
+    for kind in ('fused', 'torch'):
+        model = _train_model(S, 0.0, sd, cuda_device)
+        params = [p for n, p in model.named_parameters() if n.startswith(('vproj', 'aproj', 'transformer'))]
+        opt = (optim.FusedAdam if kind == 'fused' else torch.optim.Adam)(params, lr=3e-3, betas=(0.9, 0.999), eps=1e-7)
+        trace = []
+        for it in range(3):
+            opt.zero_grad(set_to_none=True)
+            v, a = model.project(vf, af)
+            logits = model.transformer(v, a)
+            loss = model.compute_loss(logits, targets)
+            loss.backward()
+            opt.step()
+            trace.append((float(loss), logits.detach().float().cpu()))
+        model.eval()
+        with torch.no_grad():
+            v, a = model.project(vf, af)
+            trace.append((0.0, model.transformer(v, a).float().cpu()))
+        runs[kind] = trace
+    f, t = runs['fused'], runs['torch']
+    assert (f[0][1] - f[1][1]).abs().max() > 1e-2 and (f[1][1] - f[2][1]).abs().max() > 1e-3, 'logits did not move: stale bf16 weight cache'
+    for (lf, gf), (lt, gt) in zip(f, t):
+        assert abs(lf - lt) < 2e-2 * max(1.0, abs(lt)), (lf, lt)
+        assert (gf - gt).abs().max() < 5e-2 * max(1.0, float(gt.abs().max())), float((gf - gt).abs().max())
 
 
 def test_gradients_scale_exactly_with_the_loss_scale_at_config4_size(cuda_device, monkeypatch):

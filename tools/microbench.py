@@ -53,6 +53,10 @@ def main():
             # it is a LOWER bound on what a library path would need for the fused op.  Measurement aid only, never on the product path.
             cub = timeit(lambda: torch.nn.functional.linear(a, W, bias.bfloat16()))
             res['gemm ' + name].update({'cublas_ms': cub, 'cublas_TFLOPs': fl / cub / 1e9})
+    if os.environ.get('SFB_MB_GEMM_ONLY') == '1':
+        for k, v in res.items():
+            print(f'{k:36s} ' + '  '.join(f'{kk}={vv:9.3f}' for kk, vv in v.items()))
+        return
     ms = timeit(lambda: ops.layernorm(x, g, b, 1e-6, out=ln))
     res['layernorm'] = {'ms': ms, 'GBs': M * D * 6 / ms / 1e6}
     row, seg = 3 * D, 1569 * 3 * D
