@@ -326,6 +326,18 @@ def avclip_features(sd, vis: Tensor, aud: Tensor, dtype=torch.float32):
     return F.normalize(vf, dim=-1), F.normalize(af, dim=-1)
 
 
+def avclip_loss(vfeat: Tensor, afeat: Tensor, scale, vfeat_all: Optional[Tensor] = None, afeat_all: Optional[Tensor] = None) -> Tensor:
+    """AVCLIP.compute_loss (open_clip/model.py:507-527) on L2-normalised (n, D) features: similarities of the local rows against the
+    (optionally all-gathered, :492-494) rows, divided by the temperature `scale`, soft targets `eye(n, N)` exactly as `_make_targets`
+    builds them (:515-522: the positive of local row i is column i whatever the rank), mean of the two cross-entropies."""
+    vfeat_all = vfeat if vfeat_all is None else vfeat_all
+    afeat_all = afeat if afeat_all is None else afeat_all
+    sim_v2a = vfeat @ afeat_all.mT / scale
+    sim_a2v = afeat @ vfeat_all.mT / scale
+    tgt = torch.eye(*sim_v2a.shape, dtype=sim_v2a.dtype)
+    return (F.cross_entropy(sim_v2a, tgt) + F.cross_entropy(sim_a2v, tgt)) / 2
+
+
 # ----------------------------------------------------------------------------------------------------------
 # N3 (SURVEY.md 8f): training-mode forward of the synchronisation module with EXPLICIT dropout multipliers, so that torch
 # autograd on this restatement gives the reference gradients for a known mask (scripts/train_utils.py:373-386 drives

@@ -4,18 +4,83 @@ Mirrors `AVCLIP.forward` of the reference (model/modules/feat_extractors/train_c
 forward pass in eval / no_grad: encoders with `agg_time_module='AveragePooling'` -> (B*S, 768) -> identity bridges
 (`DoNothingBridge`, configs/segment_avclip.yaml:45-54) -> L2 normalise -> similarities / logit_scale -> symmetric cross-entropy with
 identity targets.  Inputs come in the STAGE-I layouts: rgb (B, S, C=3, T=16, H, W), audio (B, S, T=66, F=128)
-(segment_avclip.yaml:208-211).  The encoders are the kernel-backed `MotionFormer` / `AST` of model.py; the 128 x 128 similarity tail is
-three tiny torch ops (normalise, matmul, cross_entropy) - plumbing next to 52 TFLOP of encoder work.
+(segment_avclip.yaml:208-211).  The encoders are the kernel-backed `MotionFormer` / `AST` of model.py; the tail (L2 normalise, similarities, symmetric
+cross-entropy and their backward) runs on the kernels of csrc/contrastive.cu; with `gather_for_loss=True` the normalised features of all
+ranks are all-gathered with an autograd-aware collective (open_clip/model.py:492-494), torch.distributed being the plumbing.
 In train mode (with autograd on) the towers take their differentiable path (train_encoders.py, SURVEY.md §8f N1: DropPath + hand-written
 backward), so `out['losses']['segment_contrastive_loss'].backward()` fills the gradients of both encoders and of `logit_scale`.
 """
 import logging
 
 import torch
-import torch.nn.functional as F
+import torch.distributed as dist
 from torch import nn
 
+from . import ops
 from .model import AST, MotionFormer
+
+
+class _L2Normalize(torch.autograd.Function):
+    """F.normalize(x, dim=-1) (open_clip/model.py:543) on (n, D) fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xn, inv = ops.l2_normalize(x.float().contiguous())
+        ctx.save_for_backward(xn, inv)
+        return xn
+
+    @staticmethod
+    def backward(ctx, g):
+        xn, inv = ctx.saved_tensors
+        return ops.l2_normalize_bwd(xn, inv, g.float().contiguous())
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """torch.distributed.nn.all_gather + cat(dim=0) (open_clip/model.py:492-494): forward all-gathers the (n, D) blocks of every rank,
+    backward returns this rank's block of the SUM over ranks of the gathered gradient (reduce-scatter)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        world, rank = dist.get_world_size(ctx.group), dist.get_rank(ctx.group)
+        g = g.contiguous()
+        n = g.shape[0] // world
+        if dist.get_backend(ctx.group) == 'gloo':            # gloo has no reduce-scatter: all-reduce and keep this rank's block
+            dist.all_reduce(g, group=ctx.group)
+            return g[rank * n:(rank + 1) * n].clone(), None
+        out = torch.empty((n,) + tuple(g.shape[1:]), device=g.device, dtype=g.dtype)
+        dist.reduce_scatter_tensor(out, g, group=ctx.group)
+        return out, None
+
+
+class _ContrastiveLoss(torch.autograd.Function):
+    """compute_loss (open_clip/model.py:507-527): one launch pair forward (similarities, softmax, loss, d loss / d sim), one backward.
+    vn_all / an_all None = no gathering: the keys are the local rows."""
+
+    @staticmethod
+    def forward(ctx, vn, an, vn_all, an_all, logit_scale):
+        local = vn_all is None
+        scale = logit_scale.detach().float().reshape(1)
+        loss, dscale, G = ops.contrastive_loss(vn, an, vn if local else vn_all, an if local else an_all, scale)
+        ctx.local = local
+        ctx.save_for_backward(vn, an, *(() if local else (vn_all, an_all)), G, scale, dscale)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        vn, an = saved[0], saved[1]
+        vn_all, an_all = (None, None) if ctx.local else (saved[2], saved[3])
+        G, scale, dscale = saved[-3:]
+        d_vn, d_an, d_vn_all, d_an_all, d_scale = ops.contrastive_loss_bwd(vn, an, vn_all, an_all, G, scale, g.float().reshape(1).contiguous(), dscale)
+        return d_vn, d_an, d_vn_all, d_an_all, d_scale.view(())
 
 
 class DoNothingBridge(nn.Identity):
@@ -51,8 +116,6 @@ class AVCLIP(nn.Module):
     def __init__(self, n_embd: int = 768, afeat_extractor=None, vfeat_extractor=None, aproj=None, vproj=None, init_scale: float = 0.07,
                  clamp_scale_min: float = 0.001, clamp_scale_max: float = 0.5, gather_for_loss: bool = False):
         super().__init__()
-        if gather_for_loss:
-            raise NotImplementedError('gather_for_loss=True (global negatives across ranks) is not implemented; segment_avclip.yaml:11 uses False')
         self.output_dict = True
         self.n_embd = n_embd
         self.v_encoder = _tower_from_config(vfeat_extractor, MotionFormer) or MotionFormer(
@@ -65,7 +128,7 @@ class AVCLIP(nn.Module):
             if cfg is not None and 'DoNothingBridge' not in str(cfg['target']):
                 raise NotImplementedError(f"bridge {cfg['target']}: only DoNothingBridge (segment_avclip.yaml:45-54) is implemented")
         self.vproj, self.aproj = DoNothingBridge(), DoNothingBridge()
-        self.clamp_scale_min, self.clamp_scale_max, self.init_scale, self.gather_for_loss = clamp_scale_min, clamp_scale_max, init_scale, False
+        self.clamp_scale_min, self.clamp_scale_max, self.init_scale, self.gather_for_loss = clamp_scale_min, clamp_scale_max, init_scale, bool(gather_for_loss)
         self.logit_scale = nn.Parameter(torch.ones([]) * init_scale)
 
     @torch.no_grad()
@@ -80,21 +143,22 @@ class AVCLIP(nn.Module):
         a, _ = self.a_encoder(aud)
         v, a = v.reshape(-1, self.n_embd), a.reshape(-1, self.n_embd)
         if do_norm:
-            v, a = F.normalize(v, dim=-1), F.normalize(a, dim=-1)
+            v, a = _L2Normalize.apply(v), _L2Normalize.apply(a)
         return v, a
 
     def forward(self, vis: torch.Tensor, aud: torch.Tensor, alpha: float = 0.0, for_loop: bool = False, world_size: int = 1):
         assert alpha == 0.0, f'alpha={alpha} not supported yet'          # same assertion as the reference (:489)
         with torch.set_grad_enabled(torch.is_grad_enabled() and self.training):     # eval: inference kernels, nothing is recorded
-            return self._forward(vis, aud)
+            return self._forward(vis, aud, world_size)
 
-    def _forward(self, vis: torch.Tensor, aud: torch.Tensor):
+    def _forward(self, vis: torch.Tensor, aud: torch.Tensor, world_size: int = 1):
         logit_scales = self.clamp_logit_scales()
         vfeat, afeat = self.encode_streams(vis, aud)
-        sim_v2a = vfeat @ afeat.mT / self.logit_scale                     # compute_loss :507-513
-        sim_a2v = afeat @ vfeat.mT / self.logit_scale
-        tgt = torch.eye(*sim_v2a.shape, device=sim_v2a.device, dtype=sim_v2a.dtype)
-        loss = (F.cross_entropy(sim_v2a, tgt) + F.cross_entropy(sim_a2v, tgt)) / 2
+        if world_size > 1 and self.gather_for_loss:                       # :492-494 global negatives; targets stay eye(n, N) as in the reference
+            vfeat_all, afeat_all = _AllGatherRows.apply(vfeat, None), _AllGatherRows.apply(afeat, None)
+        else:
+            vfeat_all, afeat_all = None, None
+        loss = _ContrastiveLoss.apply(vfeat, afeat, vfeat_all, afeat_all, self.logit_scale)          # compute_loss :507-527
         return {'rgb_features': (vfeat, None), 'audio_features': (afeat, None), 'logit_scales': logit_scales,
                 'losses': {'segment_contrastive_loss': loss}}
 

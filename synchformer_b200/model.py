@@ -93,6 +93,19 @@ def _init_from_stage1_ckpt(module: nn.Module, ckpt_path: str, encoder: str, what
     return status
 
 
+class _MeanTokens(torch.autograd.Function):
+    """AveragePooling 'BS T D -> BS D' (motionformer.py:405-409) over the 8 / 6 time tokens of a segment."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.T = x.shape[-2]
+        return ops.mean_tokens(x.float().contiguous().view(-1, x.shape[-2], x.shape[-1])).view(*x.shape[:-2], x.shape[-1])
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.mean_tokens_bwd(g.float().contiguous().view(-1, g.shape[-1]), ctx.T).view(*g.shape[:-1], ctx.T, g.shape[-1])
+
+
 def _tower_trains(m: nn.Module) -> bool:
     """A feature extractor takes the differentiable path iff it is in train mode, autograd is on and it has trainable parameters
     (stage I, or stage II with `is_trainable: True`); frozen / eval towers keep the inference path."""
@@ -280,7 +293,7 @@ class MotionFormer(_KernelModule):
         outs = [self._encode_chunk(None, P, W, a=ops.im2col_video_clip(clip[b:b + per].contiguous(), n_segments, v_start, v_stride))
                 for b in range(0, B, per)]
         feats = (outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)).view(B, n_segments, V_FRAMES, D)
-        return feats.mean(dim=2) if self.time_pool else feats
+        return _MeanTokens.apply(feats) if self.time_pool else feats
 
     def encode(self, vis: torch.Tensor) -> torch.Tensor:
         """vis (B, S, T=16, C=3, 224, 224) fp32 / fp16 / bf16 / uint8 -> (B, S, 8, 768) fp32."""
@@ -295,7 +308,7 @@ class MotionFormer(_KernelModule):
         outs = [self._encode_chunk(flat[s:s + self.max_segments_per_pass], P, W) for s in range(0, B * S, self.max_segments_per_pass)]
         feats = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
         feats = feats.view(B, S, V_FRAMES, D)
-        return feats.mean(dim=2) if self.time_pool else feats
+        return _MeanTokens.apply(feats) if self.time_pool else feats
 
 
 class AST(_KernelModule):
@@ -382,7 +395,7 @@ class AST(_KernelModule):
         kv_src = ops.layernorm(x, P['ast.layernorm.weight'], P['ast.layernorm.bias'], EPS_A, out=ln[:n * 72], rows=n * 72, group=72,
                                group_stride=A_TOK, offset=2, gamma2=P[g + 'norm1.weight'], beta2=P[g + 'norm1.bias'], eps2=EPS_V)
         feats = _cls_aggregator(P, W, g, kv_src, n, A_T, 72, 1, A_T, A_F).view(B, S, A_T, D)
-        return feats.mean(dim=2) if self.time_pool else feats
+        return _MeanTokens.apply(feats) if self.time_pool else feats
 
 
 class GlobalTransformer(_KernelModule):

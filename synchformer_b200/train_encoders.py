@@ -337,7 +337,7 @@ def ast_features(m, spec: torch.Tensor) -> torch.Tensor:
         raise ValueError(f'expected spectrogram of shape (B, S, 128, 66), got {tuple(spec.shape)}')
     B, S = spec.shape[:2]
     feats = _apply(m, _ast_forward, _ast_backward, spec.float().contiguous().view(B * S, 128, 66)).view(B, S, A_T, D)
-    return feats.mean(dim=2) if m.time_pool else feats
+    return _mean_tokens(feats) if m.time_pool else feats
 
 
 def motionformer_features(m, vis: torch.Tensor, seed: Optional[int] = None) -> torch.Tensor:
@@ -352,4 +352,9 @@ def motionformer_features(m, vis: torch.Tensor, seed: Optional[int] = None) -> t
     stochastic = bool(m.training)
     fwd = lambda mod, x: _motionformer_forward(mod, x, seed, stochastic)
     feats = _apply(m, fwd, _motionformer_backward, vis.contiguous().view(B * S, 16, 3, 224, 224)).view(B, S, V_FRAMES, D)
-    return feats.mean(dim=2) if m.time_pool else feats
+    return _mean_tokens(feats) if m.time_pool else feats
+
+
+def _mean_tokens(feats: torch.Tensor) -> torch.Tensor:
+    from .model import _MeanTokens            # model.py imports this module: resolve at call time
+    return _MeanTokens.apply(feats)

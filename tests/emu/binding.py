@@ -17,6 +17,7 @@ EMULATED = ('sfb_dropout', 'sfb_gelu_fwd', 'sfb_gelu_bwd', 'sfb_transpose_bf16',
             'sfb_layernorm_bwd', 'sfb_attention_train_fwd', 'sfb_attention_train_bwd', 'sfb_sync_head_bwd', 'sfb_last_error',
             'sfb_attention_bwd_stats_floats', 'sfb_attention_bwd', 'sfb_attention_bwd_global_query', 'sfb_droppath', 'sfb_gather_rows_bf16',
             'sfb_cross_entropy', 'sfb_optim_chunk_elems', 'sfb_grad_sqnorm', 'sfb_adam_step',
+            'sfb_mean_tokens', 'sfb_mean_tokens_bwd', 'sfb_l2_normalize', 'sfb_l2_normalize_bwd', 'sfb_contrastive_loss', 'sfb_contrastive_loss_bwd',
             # verified on the B200 in round 1 (no inline PTX): emulating them checks the emulator against kernels known to be right
             'sfb_layernorm', 'sfb_im2col_video', 'sfb_im2col_video_clip', 'sfb_video_tokens', 'sfb_im2col_ast', 'sfb_ast_tokens', 'sfb_sync_tokens',
             'sfb_sync_head', 'sfb_cast_f32_bf16',

@@ -296,6 +296,45 @@ def empty_bf16(shape, device):
     return torch.empty(shape, device=device, dtype=torch.bfloat16 if (REAL_DTYPES or ROUND_BF16) else torch.float32)
 
 
+def mean_tokens(x):
+    return x.float().mean(dim=1)
+
+
+def mean_tokens_bwd(dout, T):
+    return (dout / T).unsqueeze(1).expand(-1, T, -1).contiguous()
+
+
+def l2_normalize(x):
+    inv = 1.0 / x.norm(dim=-1).clamp_min(1e-12)
+    return x * inv.unsqueeze(1), inv
+
+
+def l2_normalize_bwd(xn, inv_norm, dxn):
+    return (dxn - xn * (xn * dxn).sum(-1, keepdim=True)) * inv_norm.unsqueeze(1)
+
+
+def contrastive_loss(vn, an, vn_all, an_all, scale):
+    n, N = vn.shape[0], vn_all.shape[0]
+    sims = torch.stack([vn @ an_all.mT, an @ vn_all.mT]) / scale                 # (2, n, N)
+    eye = torch.eye(n, N)
+    G = (torch.softmax(sims, dim=-1) - eye) * (0.5 / n)
+    loss = (-(torch.log_softmax(sims, dim=-1) * eye).sum(-1)).sum() * (0.5 / n)
+    dscale = -(G * sims).sum() / scale
+    return loss.reshape(1), dscale.reshape(1), G.contiguous()
+
+
+def contrastive_loss_bwd(vn, an, vn_all, an_all, G, scale, upstream, dscale):
+    local = vn_all is None
+    kv, ka = (vn, an) if local else (vn_all, an_all)
+    coef = upstream / scale
+    d_vn, d_an = G[0] @ ka * coef, G[1] @ kv * coef
+    d_ka, d_kv = G[0].mT @ vn * coef, G[1].mT @ an * coef
+    if local:
+        return d_vn + d_kv, d_an + d_ka, None, None, dscale * upstream
+    return d_vn, d_an, d_kv, d_ka, dscale * upstream
+
+
+CONTRASTIVE = ('mean_tokens', 'mean_tokens_bwd', 'l2_normalize', 'l2_normalize_bwd', 'contrastive_loss', 'contrastive_loss_bwd')
 N1_BWD = ('attention_bwd', 'attention_bwd_global_query', 'droppath', 'gather_rows_bf16', 'empty_bf16')
 ENCODER_FWD = ('im2col_video', 'video_tokens', 'im2col_ast', 'ast_tokens', 'attention')
 

@@ -160,7 +160,7 @@ def test_avclip_train_mode_routes_through_the_differentiable_towers(monkeypatch)
     calls = []
     monkeypatch.setattr(TE, 'motionformer_features', lambda m, vis: (calls.append('v'), torch.zeros(vis.shape[0], vis.shape[1], 768, requires_grad=True))[1])
     monkeypatch.setattr(TE, 'ast_features', lambda m, spec: (calls.append('a'), torch.ones(spec.shape[0], spec.shape[1], 768, requires_grad=True))[1])
-    fake_ops.install(monkeypatch, names=('require_cuda',))
+    fake_ops.install(monkeypatch, names=('require_cuda',) + fake_ops.CONTRASTIVE)
     model = avclip.AVCLIP().train()
     out = model(torch.zeros(1, 2, 3, 16, 224, 224), torch.zeros(1, 2, 66, 128))
     assert calls == ['v', 'a'] and out['losses']['segment_contrastive_loss'].requires_grad
@@ -219,3 +219,67 @@ def test_mma_attention_backward_matches_cuda_core_kernels_and_autograd(monkeypat
         if prefix:
             assert float((res[name][1] - ref_part).norm() / ref_part.norm()) < 6e-3, name
     assert float((res['mma'][0][:, cols].float() - res['cuda'][0][:, cols].float()).norm() / r.norm()) < 6e-3
+
+
+@pytest.mark.parametrize('n,N', [(6, 6), (5, 15)])
+def test_contrastive_tail_kernels_on_the_emulator(monkeypatch, n, N):
+    """the real sources of csrc/contrastive.cu on the CPU SIMT emulator, checked by the same test body that runs on the B200"""
+    import test_train_encoders_gpu as G
+    binding.install(monkeypatch)
+    with torch.enable_grad():
+        G.test_contrastive_tail_kernels_match_oracle_autograd(torch.device('cpu'), n, N)
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    mp = pytest.MonkeyPatch()
+    fake_ops.install(mp, names=('require_cuda',) + fake_ops.CONTRASTIVE)
+    from synchformer_b200 import avclip
+    g = torch.Generator().manual_seed(5)
+    v_all, a_all = torch.randn(world * 3, 768, generator=g), torch.randn(world * 3, 768, generator=g)
+    v = v_all[rank * 3:(rank + 1) * 3].clone().requires_grad_(True)
+    a = a_all[rank * 3:(rank + 1) * 3].clone().requires_grad_(True)
+    scale = torch.tensor(0.07, requires_grad=True)
+    with torch.enable_grad():
+        vn, an = avclip._L2Normalize.apply(v), avclip._L2Normalize.apply(a)
+        loss = avclip._ContrastiveLoss.apply(vn, an, avclip._AllGatherRows.apply(vn, None), avclip._AllGatherRows.apply(an, None), scale)
+        loss.backward()
+    q.put((rank, loss.detach(), v.grad, a.grad, scale.grad))
+    dist.barrier()
+    dist.destroy_process_group()
+    mp.undo()
+
+
+def test_gather_for_loss_matches_the_reference_formulation_on_two_ranks():
+    """gather_for_loss=True (open_clip/model.py:492-494) under world_size-2 gloo: every rank's loss and gradients equal torch autograd on
+    the oracle's restatement where the gathered features are differentiable on EVERY rank (torch.distributed.nn.all_gather semantics: the
+    backward of the gather sums the ranks' gradients for each block)."""
+    import torch.multiprocessing as tmp
+    world = 2
+    ctx = tmp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = {r[0]: r[1:] for r in (q.get(timeout=240) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(5)
+    v_all = torch.randn(world * 3, 768, generator=g).requires_grad_(True)
+    a_all = torch.randn(world * 3, 768, generator=g).requires_grad_(True)
+    scale = torch.tensor(0.07, requires_grad=True)
+    with torch.enable_grad():
+        vn, an = torch.nn.functional.normalize(v_all, dim=-1), torch.nn.functional.normalize(a_all, dim=-1)
+        losses = [O.avclip_loss(vn[r * 3:(r + 1) * 3], an[r * 3:(r + 1) * 3], scale, vn, an) for r in range(world)]
+        sum(losses).backward()               # DDP averages afterwards; the sum over ranks is what the per-rank backward passes add up to
+    for r in range(world):
+        loss, gv, ga, gs = outs[r]
+        assert abs(float(loss) - float(losses[r])) < 1e-5
+        assert (gv - v_all.grad[r * 3:(r + 1) * 3]).abs().max() < 1e-5 * max(1.0, float(v_all.grad.abs().max()))
+        assert (ga - a_all.grad[r * 3:(r + 1) * 3]).abs().max() < 1e-5 * max(1.0, float(a_all.grad.abs().max()))
+    # d logit_scale is local to each rank's loss (DDP all-reduces it later): the two add up to the oracle's
+    assert abs(sum(float(outs[r][3]) for r in range(world)) - float(scale.grad)) < 1e-4 * max(1.0, abs(float(scale.grad)))

@@ -170,3 +170,39 @@ def test_shifted_window_eval(cuda_device):
     assert torch.equal(pv.cpu()[clear], rv[clear])
     gt = torch.arange(S - W + 1).view(1, -1)
     assert (pv.cpu() == gt).float().mean() > 0.9 and (pa.cpu() == gt).float().mean() > 0.9
+
+
+@pytest.mark.parametrize('n,N', [(6, 6), (5, 15), (128, 128)])
+def test_contrastive_tail_kernels_match_oracle_autograd(cuda_device, n, N):
+    """csrc/contrastive.cu (mean pooling, L2 normalise, similarities + symmetric CE, backward) against torch autograd on the oracle's
+    restatement of open_clip/model.py:507-545; N > n stands for gathered features of other ranks (eye(n, N) targets as in the reference)."""
+    dev = cuda_device
+    if n > 16 and dev.type != 'cuda':
+        pytest.skip('large case on hardware only')
+    g = torch.Generator().manual_seed(n * 31 + N)
+    T, Dm = 8, 768
+    xv = torch.randn(n, T, Dm, generator=g, requires_grad=True)
+    xa = torch.randn(n, 6, Dm, generator=g, requires_grad=True)
+    others_v = torch.nn.functional.normalize(torch.randn(N - n, Dm, generator=g), dim=-1)
+    others_a = torch.nn.functional.normalize(torch.randn(N - n, Dm, generator=g), dim=-1)
+    scale = torch.tensor(0.07, requires_grad=True)
+    # oracle
+    vn, an = torch.nn.functional.normalize(xv.mean(1), dim=-1), torch.nn.functional.normalize(xa.mean(1), dim=-1)
+    v_all, a_all = torch.cat([vn, others_v]), torch.cat([an, others_a])
+    ref = O.avclip_loss(vn, an, scale, v_all if N > n else None, a_all if N > n else None)
+    ref_grads = torch.autograd.grad(ref * 3.0, [xv, xa, scale])
+    # kernels
+    dxv, dxa = xv.detach().to(dev).requires_grad_(True), xa.detach().to(dev).requires_grad_(True)
+    dscale = scale.detach().to(dev).requires_grad_(True)
+    kvn, kan = avclip._L2Normalize.apply(M._MeanTokens.apply(dxv)), avclip._L2Normalize.apply(M._MeanTokens.apply(dxa))
+    assert (kvn.detach().cpu() - vn.detach()).abs().max() < 1e-6
+    if N > n:
+        kv_all, ka_all = torch.cat([kvn, others_v.to(dev)]), torch.cat([kan, others_a.to(dev)])
+        loss = avclip._ContrastiveLoss.apply(kvn, kan, kv_all, ka_all, dscale)
+    else:
+        loss = avclip._ContrastiveLoss.apply(kvn, kan, None, None, dscale)
+    grads = torch.autograd.grad(loss * 3.0, [dxv, dxa, dscale])
+    assert abs(float(loss) - float(ref)) < 2e-5 * max(1.0, abs(float(ref)))
+    for got, want, name in zip(grads, ref_grads, ('d video tokens', 'd audio tokens', 'd logit_scale')):
+        err = float((got.cpu() - want).abs().max())
+        assert err <= 2e-4 * float(want.abs().max()) + 1e-7, (name, err, float(want.abs().max()))

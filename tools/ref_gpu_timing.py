@@ -44,6 +44,7 @@ def time_config(model, B, S, ctx_name, dev, iters=10, warm=3):
 
 
 def main():
+    out = os.path.abspath(sys.argv[1]) if len(sys.argv) > 1 else os.path.join(REPO, 'gpurun_out', 'reference_gpu.json')      # before import_reference() chdirs
     import _ref_import
     from synchformer_b200 import synth
     assert _ref_import.reference_available(), f"no reference at {os.environ['SYNCHFORMER_REF']} (run tools/make_baseline_ref.py where /root/reference exists)"
@@ -76,7 +77,6 @@ def main():
             res[f'best_S{S}_{name}'] = best
         del model
         torch.cuda.empty_cache()
-    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(REPO, 'gpurun_out', 'reference_gpu.json')
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, 'w') as f:
         json.dump(res, f, indent=1)
