@@ -8,8 +8,9 @@ fp16 RGB segments -> Motionformer, AST, CLS aggregators, projections, [all-gathe
 sync transformer -> (B, 21) logits.  Workload at N = 1 is BASELINE.json configs[1]: sync.yaml inference, batch 64,
 8 segments / clip, bf16.  Scaling is weak: every rank processes `--batch` clips, `value` = all clips / max-over-ranks time.
 
-Rank 0 prints ONE JSON line (see the keys in main()).  `--impl reference` times the CPU oracle restatement of the reference
-(`oracle/`, "port": the Python reference cannot travel to the GPU box) on the host cores, rank 0 only.
+Rank 0 prints ONE JSON line (see the keys in main()).  `--impl reference` times the reference's CPU path on the host cores, rank 0 only: the UNMODIFIED
+reference staged under the git-ignored baseline/_ref (tools/make_baseline_ref.py; kind "reference") or, where that is absent, the CPU
+oracle restatement (`oracle/`, kind "port").
 """
 import argparse
 import json
@@ -73,24 +74,63 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm)}
 
 
-def cpu_oracle_clips_per_sec(S: int, n_clips: int, steps: int, warmup: int):
-    """The reference's algorithm on the host cores: the torch-CPU oracle port, fp32, all threads, bounded sample."""
-    from oracle import synchformer_oracle as O
+def _staged_reference_root():
+    """The unmodified reference staged by tools/make_baseline_ref.py under the git-ignored baseline/_ref (it travels with the gpurun
+    snapshot; /root/reference does not exist on the GPU box)."""
+    root = os.path.join(REPO, 'baseline', '_ref')
+    return root if os.path.isdir(os.path.join(root, 'model')) else None
+
+
+def cpu_reference_clips_per_sec(S: int, n_clips: int, steps: int, warmup: int):
+    """The reference's own CPU path on the host cores, fp32, all threads, bounded sample.  kind 'reference': the UNMODIFIED reference
+    (baseline/_ref: its transform tail dataset/transforms.py:815-871 + model.sync_model.Synchformer.forward) when it is staged; else kind
+    'port': the torch-CPU oracle restatement.  Returns (clips/s, seconds per step, kind, description)."""
     from synchformer_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.synthetic_state_dict(1337, n_segments=S)
     vis = synth.synthetic_video(n_clips, S, 0)
     wave = synth.synthetic_waveform(n_clips, S, 0)
+    root = _staged_reference_root()
+    cwd = os.getcwd()
+    if root is not None:
+        os.environ['SYNCHFORMER_REF'] = root
+        sys.path.insert(0, os.path.join(REPO, 'tests', 'golden'))
+        import importlib
+        import _ref_import
+        _ref_import.REF_ROOT = root
+        model = _ref_import.build_reference_model(S)
+        model.load_state_dict(sd, strict=True)
+        T = importlib.import_module('dataset.transforms')
+        chain = [T.AudioMelSpectrogram(sample_rate=16000, win_length=400, hop_length=160, n_fft=1024, n_mels=128), T.AudioLog(),
+                 T.PadOrTruncate(max_spec_t=66), T.AudioNormalizeAST(mean=-4.2677393, std=4.5689974)]          # configs/sync.yaml:183-197
+
+        def step():
+            auds = []
+            for b in range(n_clips):
+                item = {'audio': wave[b], 'meta': {'audio': {}}}
+                for t in chain:
+                    item = t(item)
+                auds.append(item['audio'])
+            return model(vis, torch.stack(auds).unsqueeze(2))[1]                                             # (B, S, 1, F, T)
+        kind, what = 'reference', 'UNMODIFIED reference (baseline/_ref): torchaudio mel transform tail + model.sync_model.Synchformer.forward'
+    else:
+        from oracle import synchformer_oracle as O
+
+        def step():
+            return O.forward(sd, vis, O.mel_frontend(wave).float().unsqueeze(2))[1]
+        kind, what = 'port', 'torch CPU oracle port of the reference forward (mel + encoders + sync)'
     times = []
-    with torch.no_grad():
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            aud = O.mel_frontend(wave).float().unsqueeze(2)
-            O.forward(sd, vis, aud)
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
+    try:
+        with torch.no_grad():
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                step()
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
+    finally:
+        os.chdir(cwd)                       # importing the reference changes the working directory
     sec = sum(times) / len(times)
-    return n_clips / sec, sec
+    return n_clips / sec, sec, kind, what
 
 
 def run_reference(args, rank: int):
@@ -98,42 +138,78 @@ def run_reference(args, rank: int):
         return
     cores = os.cpu_count() or 1
     n_clips = 1
-    value, sec = cpu_oracle_clips_per_sec(args.segments, n_clips, max(1, min(args.steps, 2)), min(args.warmup, 1))
-    sample = f'{n_clips} clip x {args.segments} segments per step, fp32, torch CPU oracle port of the reference forward (mel + encoders + sync)'
+    value, sec, kind, what = cpu_reference_clips_per_sec(args.segments, n_clips, max(1, min(args.steps, 2)), min(args.warmup, 1))
+    sample = f'{n_clips} clip x {args.segments} segments per step, fp32, {what}'
     print(json.dumps({
         'impl': 'reference', 'metric': 'clips/sec offset inference (5s-style clip: S x 0.64 s segments, 224p RGB + 16 kHz)', 'value': value,
         'unit': 'clips/s', 'n_gpus': args.gpus, 'steps': max(1, min(args.steps, 2)), 'warmup': min(args.warmup, 1), 'ms_per_step': sec * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'sync.yaml inference, batch={args.batch}, {args.segments} segments/clip (CPU sample: {n_clips} clip/step)'},
-        'cpu_baseline': {'value': value, 'unit': 'clips/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'clips/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }), flush=True)
 
 
 class GemmTimer:
-    """CUDA-event timing of every GEMM launch inside the timed region, on the launching stream (roofline.achieved)."""
+    """CUDA-event timing of every launch of the hot kernels inside the timed region, on the launching stream: the GEMM (roofline.achieved:
+    algorithmic FLOPs / time) and the HBM-bound kernel classes around it (attention by shape class, LayerNorm: algorithmic bytes / time)."""
 
     def __init__(self, ops):
-        self.ops, self.records, self.orig = ops, [], ops.gemm
+        self.ops, self.records, self.other = ops, [], {}
+        self.orig = {n: getattr(ops, n) for n in ('gemm', 'attention', 'layernorm', 'rowstats_cast')}
 
-    def __enter__(self):
-        def timed(a, w, bias, out=None, **kw):
+    def _timed(self, fn, key_work):
+        def wrapper(*a, **kw):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            r = self.orig(a, w, bias, out, **kw)
+            r = fn(*a, **kw)
             e.record()
-            self.records.append((2.0 * a.shape[0] * w.shape[0] * w.shape[1], s, e))
+            key, work = key_work(*a, **kw)
+            if key == 'gemm':
+                self.records.append((work, s, e))
+            else:
+                self.other.setdefault(key, []).append((work, s, e))
             return r
-        self.ops.gemm = timed
+        return wrapper
+
+    def __enter__(self):
+        def gemm_work(a, w, bias, out=None, **kw):
+            return 'gemm', 2.0 * a.shape[0] * w.shape[0] * w.shape[1]
+
+        def attn_work(q, k, v, out, *, n_outer, n_inner, n_heads, head_dim, Lq, Lk, k_prefix=None, **kw):
+            cls = 'attn_space_196x197' if Lq == 196 else 'attn_time_8x9' if (Lq == 8 and Lk == 8) else 'attn_cls_row' if Lq == 1 else f'attn_{Lq}x{Lk}_hd{head_dim}'
+            rows = n_outer * n_inner * n_heads * (2 * Lq + 2 * Lk) + (2 * n_outer * n_heads if k_prefix is not None else 0)
+            return cls, float(rows * head_dim * 2)                     # q + out rows, k + v rows (bf16), every row once
+
+        def ln_work(x, *a, rows=None, out_f32=False, **kw):
+            r = x.shape[0] if rows is None else rows
+            return 'layernorm', float(r * 768 * (4 + (4 if out_f32 else 2)))
+
+        def rs_work(x, *a, **kw):
+            return 'layernorm', float(x.shape[0] * 768 * 6)
+
+        for name, kw in (('gemm', gemm_work), ('attention', attn_work), ('layernorm', ln_work), ('rowstats_cast', rs_work)):
+            setattr(self.ops, name, self._timed(self.orig[name], kw))
         return self
 
     def __exit__(self, *exc):
-        self.ops.gemm = self.orig
+        for name, fn in self.orig.items():
+            setattr(self.ops, name, fn)
 
     def summary(self):
         flops = sum(f for f, _, _ in self.records)
         ms = sum(s.elapsed_time(e) for _, s, e in self.records)
         return flops, ms, len(self.records)
+
+    def hbm_kernels(self, steps: int, hbm_peak_gbs: float):
+        """per kernel class: launches / step, ms / step, achieved GB/s of ALGORITHMIC bytes (every operand row once), fraction of the measured copy peak"""
+        out = {}
+        for key, recs in sorted(self.other.items()):
+            ms = sum(s.elapsed_time(e) for _, s, e in recs)
+            nbytes = sum(b for b, _, _ in recs)
+            gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else None
+            out[key] = {'launches_per_step': len(recs) / steps, 'ms_per_step': ms / steps, 'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / hbm_peak_gbs if gbs else None}
+        return out
 
 
 def main():
@@ -260,7 +336,7 @@ def main():
         e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         traffic, traffic_note = None, None
-        tp = os.path.join(REPO, 'profiles', 'r1_gemm_traffic.json')
+        tp = os.path.join(REPO, 'profiles', 'r2_gemm_traffic.json')
         if os.path.exists(tp):                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu capture
             tj = json.load(open(tp))
             traffic, traffic_note = tj['dram_bytes'], f"{tj['launch']}; algorithmic bytes {tj['algorithmic_bytes']}; {tj['source']}"
@@ -278,7 +354,11 @@ def main():
                          'kernel': 'gemm_bf16_tcgen05_kernel', 'launches_timed': gemm_n, 'gemm_ms_per_step': gemm_ms / args.steps,
                          'peak_source': peaks['source'] + ', sustained bf16 (kernel timed inside a long step)',
                          'step_frac_canonical': value * flops_per_clip(S) / world / (peaks['sustained'] * 1e12),
-                         'flops_per_clip_canonical': flops_per_clip(S)},
+                         'step_frac_note': 'whole step (all kernels) against the canonical reference FLOP count; `frac` above is the dominant kernel alone',
+                         'flops_per_clip_canonical': flops_per_clip(S),
+                         # the MHSA / LayerNorm kernels are HBM-bound (AI of the 196 x 197 space attention ~ 99 FLOP/B against a ridge of 223),
+                         # so their roofline is the measured copy bandwidth, not the tensor pipe
+                         'hbm_bound_kernels': gt.hbm_kernels(args.steps, peaks['hbm']), 'hbm_peak_gbs': peaks['hbm']},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'clips/s', 'h2d_bytes_per_step': vis_h.numel() * vis_h.element_size() + wave_h.numel() * 4,
                     'd2h_bytes_per_step': out_h.numel() * 4, 'steps': e2e_steps},
@@ -286,9 +366,9 @@ def main():
             'logits_checksum': float(logits.float().abs().sum()),
         }
         if world == 1 and not args.no_cpu_baseline:
-            cv, csec = cpu_oracle_clips_per_sec(S, 1, 1, 0)
-            result['cpu_baseline'] = {'value': cv, 'unit': 'clips/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
-                                      'sample': f'1 clip x {S} segments, fp32 torch CPU oracle port of the reference forward, {csec:.1f} s'}
+            cv, csec, ckind, cwhat = cpu_reference_clips_per_sec(S, 1, 1, 0)
+            result['cpu_baseline'] = {'value': cv, 'unit': 'clips/s', 'cores': os.cpu_count() or 1, 'kind': ckind,
+                                      'sample': f'1 clip x {S} segments, fp32, {cwhat}, {csec:.1f} s'}
         print(json.dumps(result), flush=True)
     if world > 1:
         dist.barrier()

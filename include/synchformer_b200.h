@@ -51,8 +51,26 @@ int sfb_device_check(void);
 #define SFB_GEMM_GELU 1
 #define SFB_GEMM_RESIDUAL 2
 #define SFB_GEMM_OUT_F32 4
+#define SFB_GEMM_EMIT_LN 8
+#define SFB_GEMM_LN_FOLD 16
 int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const float *bias, const float *residual, int64_t ldr,
                   void *out, int64_t ldo, int M, int N, int K, int flags, int impl, void *stream);
+
+/* K5 + K4 fused: nn.LayerNorm folded into the Linear on either side of it (DividedSpaceTimeBlock.forward vit_helper.py:364-376:
+ * norm3 -> timeattn.qkv, norm1 -> attn.qkv, norm2 -> mlp.fc1, each fed by the residual update before it).  Same as sfb_gemm_bf16 plus
+ *   SFB_GEMM_EMIT_LN  (with RESIDUAL | OUT_F32, N % 64 == 0): also writes emit_bf16[M, N] = bf16(out) (row stride ld_emit) and
+ *                     emit_stats[M][N / 64][2] = (sum, sum of squares) of the fp32 out row over each 64-column group
+ *   SFB_GEMM_LN_FOLD  (bf16 output): A holds UN-normalised rows, W = bf16(gamma . W0), bias = b0 + W0 beta, ln_colsum[N] = row sums of W
+ *                     as stored (bf16 values, fp32 sum), ln_stats[M][ln_parts][2] partial (sum, sum of squares) of the A rows over K;
+ *                         out = epilogue( rstd (A W^T - mean ln_colsum) + bias ),  mean = sum / K,  rstd = rsqrt(sumsq / K - mean^2 + ln_eps)
+ *                     which equals LayerNorm(A; gamma, beta, ln_eps) W0^T + b0 with bf16 operand rounding applied to A instead of to
+ *                     the normalised rows. */
+int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const float *bias, const float *residual, int64_t ldr,
+                     void *out, int64_t ldo, int M, int N, int K, int flags, int impl, const float *ln_stats, int ln_parts,
+                     const float *ln_colsum, float ln_eps, float *emit_stats, void *emit_bf16, int64_t ld_emit, void *stream);
+/* x (rows, 768) fp32 (row stride ldx) -> xb (rows, 768) bf16 contiguous and stats[rows][1][2] = (sum, sum of squares) per row: the
+ * LN_FOLD inputs for a residual stream that no EMIT_LN GEMM produced (the token assembly before block 0). */
+int sfb_rowstats_cast(const float *x, int64_t ldx, void *xb, float *stats, int rows, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K4 — nn.LayerNorm over D = 768 with fp32 statistics (eps 1e-6 Motionformer/aggregators

@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libsynchformer_b200.so')
 
-SFB_GEMM_GELU, SFB_GEMM_RESIDUAL, SFB_GEMM_OUT_F32 = 1, 2, 4
+SFB_GEMM_GELU, SFB_GEMM_RESIDUAL, SFB_GEMM_OUT_F32, SFB_GEMM_EMIT_LN, SFB_GEMM_LN_FOLD = 1, 2, 4, 8, 16
 
 
 class AttnDesc(Structure):
@@ -36,6 +36,9 @@ SIGNATURES = {
     'sfb_device_check': (c_int, []),
     'sfb_gemm_bf16': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                               c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'sfb_gemm_bf16_ln': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                 c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
+    'sfb_rowstats_cast': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     'sfb_layernorm': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float,
                               c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
     'sfb_attention': (c_int, [POINTER(AttnDesc), c_void_p]),

@@ -19,6 +19,12 @@
 //                              shared-memory buffer, then row-contiguous residual loads and 16-byte stores;
 //                              the 512 TMEM columns hold TWO 128x256 fp32 accumulators so the epilogue of tile i
 //                              overlaps the main loop of tile i+1
+// LayerNorm fusion (the 36 LayerNorm passes of the Motionformer blocks disappear; vit_helper.py:366-375):
+//   SFB_GEMM_EMIT_LN  a residual GEMM (proj / fc2) also writes a bf16 copy xb of its fp32 output rows and, per row and 64-column group,
+//                     (sum, sum of squares) of the fp32 values: the LayerNorm statistics of the NEXT norm, for free in the epilogue
+//   SFB_GEMM_LN_FOLD  the consumer (qkv / fc1) multiplies the UN-normalised xb by weights with gamma folded in and applies
+//                         out = rstd_row (acc - mean_row colsum_j) + bias'_j        colsum_j = sum_k bf16(gamma_k W_jk),  bias' = b + W beta
+//                     in its epilogue - algebraically LayerNorm(x) W^T + b with the same bf16 operand rounding budget as the unfused path
 // Tiles are walked n-fastest so the CTAs that share an A row-block run at the same time and hit it in L2;
 // W (<= 4.7 MB) is L2-resident throughout.  M / N / K tails are handled by TMA zero fill + epilogue masking.
 //
@@ -70,6 +76,14 @@ struct EpiParams {
     int flags;
     int num_m_blocks, num_n_blocks;
     int m_fastest;   // tile walk order (experiment switch SFB_GEMM_ORDER=1); default n-fastest
+    // LayerNorm fusion
+    const float *ln_stats;    // LN_FOLD: [M][ln_parts][2] partial (sum, sum of squares) of the rows of A over its K columns
+    const float *ln_colsum;   // LN_FOLD: [N] column sums of the folded bf16 weights
+    int ln_parts;
+    float ln_eps;
+    float *emit_stats;        // EMIT_LN: [M][N / 64][2]
+    __nv_bfloat16 *emit_bf16; // EMIT_LN: bf16 copy of the output rows, row stride ld_emit
+    int64_t ld_emit;
 };
 
 // ------------------------------------------------------------------------------------------ cluster helpers
@@ -112,25 +126,22 @@ __device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t cta_mask)
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
                  : "memory");
 }
-// TMA load multicast to the CTAs of `cta_mask` (same CTA-relative smem offset in each); with cta_group::2 the completion is
-// signalled on the barrier at `bar`'s offset in the LEADER of each destination CTA's pair (bar = local address with the peer bit cleared)
-__device__ __forceinline__ void tma_load_2d_cg2_mc(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
-        : "memory");
-}
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the bit that distinguishes the two CTAs of a pair in a shared-window address
 
 // ------------------------------------------------------------------------------------------------ the kernel
-// CL = CTAs per cluster.  CL == 4 (with CG == 2): two CTA pairs stacked along M share every W tile - each CTA fetches a quarter of it
-// and multicasts it to the CTA of the same parity in the other pair, cutting L2->SM operand traffic from 64 to 48 bytes per MMA clock.
-template <int CG, int CL>
+// CG = CTAs per cluster (1, or a cta_group::2 pair).  EPI selects the epilogue at compile time (each variant gets its own register
+// allocation under the 96-register cap of a 576-thread CTA):
+//   EPI_BF16     bf16 output (bias, optional GELU)                 EPI_BF16_LN  the same behind a folded LayerNorm (SFB_GEMM_LN_FOLD)
+//   EPI_F32      fp32 output (bias, optional GELU / residual)      EPI_F32_LN   the same + bf16 copy and row statistics (SFB_GEMM_EMIT_LN)
+// (A third cluster shape - two pairs sharing every W tile through TMA multicast, 48 instead of 64 bytes of L2 reads per MMA clock - was
+// built and measured 3-8 % slower in round 1: multicast removes L2 reads, not bytes entering the SM, and 4-CTA clusters strand SMs.)
+enum { EPI_BF16 = 0, EPI_BF16_LN = 1, EPI_F32 = 2, EPI_F32_LN = 3 };
+
+template <int CG, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)   // 18 warps are allocated as 20 (granularity 4): 96 registers per thread
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const EpiParams p) {
-    static_assert(CL == CG || (CG == 2 && CL == 4), "cluster = one CTA, one pair, or two pairs");
     using C = Cfg<CG>;
-    constexpr int PAIRS = CL / CG;                    // CTA groups per cluster, stacked along M
+    constexpr int CL = CG;
     constexpr int kStages = C::kStages;
     constexpr uint32_t STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -139,9 +150,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;     // rank in the cluster
-    const uint32_t rank = crank & 1u;                            // rank in the pair; 0 is the MMA leader
-    const uint32_t pair = crank >> 1;                            // which pair of the cluster
+    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;     // rank in the cluster = rank in the pair; 0 is the MMA leader
+    const uint32_t rank = crank;
     const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -156,7 +166,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar(s), 1);     // the (leader's) producer arrive.expect_tx; TMA of both CTAs completes the bytes
-            mbar_init(empty_bar(s), PAIRS); // one tcgen05.commit per pair of the cluster (each pair also reads what the others multicast)
+            mbar_init(empty_bar(s), 1);    // the tcgen05.commit of the (pair's) MMA issuer
         }
         for (int a = 0; a < kAccStages; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -180,7 +190,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;       // tiles of (128 * CG) x 256
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;     // a tile is (128 * CG * PAIRS) rows x 256 columns
+    const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;     // a tile is (128 * CG) rows x 256 columns
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -188,8 +198,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         uint32_t phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CL) + crank * BLOCK_M;
-            int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + rank * C::B_ROWS * (CG - 1) +
-                     (PAIRS == 2 ? pair * (C::B_ROWS / 2) : 0);          // CL == 4: this CTA fetches one 64-row quarter of the W tile
+            int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + rank * C::B_ROWS * (CG - 1);
             if (lane == 0) {
                 // a box that lies completely outside the matrix (second CTA of a pair on a ragged edge) loads rows 0.. instead:
                 // its products only reach accumulator rows / columns that the epilogue masks
@@ -203,11 +212,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         const uint32_t fb = full_bar(stage) & kPeerBitMask;                   // the pair leader's barrier
                         if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);   // bytes landing in both CTAs of the pair
                         tma_load_2d_cg2(sa, &tmap_a, fb, kb * BLOCK_K, m0);
-                        if (PAIRS == 2)     // quarter of the W tile -> same-parity CTA of both pairs
-                            tma_load_2d_cg2_mc(sa + A_BYTES + pair * (C::B_BYTES / 2), &tmap_w, fb, kb * BLOCK_K, n0,
-                                               static_cast<uint16_t>((1u << rank) | (1u << (rank + 2))));
-                        else
-                            tma_load_2d_cg2(sa + A_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+                        tma_load_2d_cg2(sa + A_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
                     } else {
                         mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
                         tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m0);
@@ -242,13 +247,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, static_cast<uint32_t>((kb | k) != 0));
                         else umma_bf16(tmem_d, da, db, idesc, static_cast<uint32_t>((kb | k) != 0));
                     }
-                    if (CG == 2) umma_commit_cg2(empty_bar(stage), static_cast<uint16_t>((1u << CL) - 1)); else umma_commit(empty_bar(stage));   // smem stage reusable
+                    if (CG == 2) umma_commit_cg2(empty_bar(stage), static_cast<uint16_t>(3u)); else umma_commit(empty_bar(stage));   // smem stage reusable
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                if (CG == 2) umma_commit_cg2(tfull_bar(acc), static_cast<uint16_t>(3u << (2 * pair))); else umma_commit(tfull_bar(acc));   // accumulator complete (own pair)
+                if (CG == 2) umma_commit_cg2(tfull_bar(acc), static_cast<uint16_t>(3u)); else umma_commit(tfull_bar(acc));   // accumulator complete
                 if (++acc == kAccStages) {
                     acc = 0;
                     acc_phase ^= 1u;
@@ -264,14 +269,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int quarter = (warp - 2) >> 2;  // which 64 of the 256 accumulator columns
         const bool gelu = (p.flags & SFB_GEMM_GELU) != 0;
         const bool has_res = (p.flags & SFB_GEMM_RESIDUAL) != 0 && !(p.flags & DBG_NORES);
-        const bool out_f32 = (p.flags & SFB_GEMM_OUT_F32) != 0;
+        constexpr bool out_f32 = EPI == EPI_F32 || EPI == EPI_F32_LN;
+        constexpr bool ln_fold = EPI == EPI_BF16_LN;
+        constexpr bool emit_ln = EPI == EPI_F32_LN;
         const bool do_store = !(p.flags & DBG_NOSTORE);
+        const float inv_k = 1.0f / static_cast<float>(p.K);
         uint8_t *stage = smem_raw + (tiles_base - smem_u32(smem_raw)) + kStages * STAGE_BYTES + (warp - 2) * EPI_WARP_BYTES;
         uint8_t *st_row = stage + lane * 128;                 // this thread's accumulator row in the transpose buffer
         const int rr = lane >> 3, cc = lane & 7;              // read-back mapping: rows 4i + rr, 16-byte chunk cc
         int acc = 0;
         uint32_t acc_phase = 0;
-        const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(tempty_bar(0), crank & ~1u) : tempty_bar(0);
+        const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(tempty_bar(0), 0u) : tempty_bar(0);
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             const int m0 = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CL) + crank * BLOCK_M + q * 32;
             const int n0 = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + quarter * 64;
@@ -290,7 +298,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            if (out_f32 && has_res) load_res(0);
+            if (out_f32 && has_res) {
+                load_res(0);
+                // chunk 1's residual rows are requested only after chunk 0's registers are free: pull their lines into L2 now
+                // (no registers needed), so that second request is an L2 hit instead of a DRAM round trip
+                if (p.ldr != 0 && n0 + 32 + cc * 4 < p.N) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int64_t grow = m0 + 4 * i + rr;
+                        if (grow < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + grow * p.ldr + n0 + 32 + cc * 4));
+                    }
+                }
+            }
+            // LN_FOLD: mean / rstd of this thread's accumulator row from the partial sums the producer GEMM (or sfb_rowstats_cast) left
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if (ln_fold) {
+                const int64_t grow = m0 + lane;
+                if (grow < p.M) {
+                    const float *sp = p.ln_stats + grow * p.ln_parts * 2;
+                    float s1 = 0.f, s2 = 0.f;
+                    if ((p.ln_parts & 1) == 0) {
+                        for (int t = 0; t < p.ln_parts; t += 2) {
+                            const float4 u = __ldg(reinterpret_cast<const float4 *>(sp + 2 * t));
+                            s1 += u.x + u.z, s2 += u.y + u.w;
+                        }
+                    } else {
+                        for (int t = 0; t < p.ln_parts; ++t) {
+                            const float2 u = __ldg(reinterpret_cast<const float2 *>(sp + 2 * t));
+                            s1 += u.x, s2 += u.y;
+                        }
+                    }
+                    ln_mean = s1 * inv_k;
+                    ln_rstd = rsqrtf(fmaxf(fmaf(-ln_mean, ln_mean, s2 * inv_k), 0.f) + p.ln_eps);
+                }
+            }
+            float ln_ps = 0.f, ln_pq = 0.f;     // EMIT_LN: this lane's row (4 cc + rr) summed over the warp's 64 columns
             // The accumulator is handed back to the MMA issuer as soon as this warp's LAST tcgen05.ld of the tile has completed - the
             // bias / GELU / transpose / global stores that follow work on registers only.  (Releasing at the end of the epilogue, with a
             // release-ordered remote arrive behind the global stores, showed up as ~10 % of the stall samples and kept tile i+2's
@@ -339,14 +381,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             const int rloc = 4 * i + rr;
                             const int64_t grow = m0 + rloc;
                             float4 val = *reinterpret_cast<const float4 *>(stage + rloc * 128 + ((cc ^ (rloc & 7)) << 4));
-                            if (grow < p.M && gcol < p.N) {
+                            const bool inb = grow < p.M && gcol < p.N;
+                            if (inb) {
                                 if (has_res) val.x += res[i].x, val.y += res[i].y, val.z += res[i].z, val.w += res[i].w;
                                 if (do_store) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + grow * p.ldo + gcol) = val;
+                            }
+                            if (emit_ln) {          // warp-uniform
+                                if (inb && do_store)
+                                    *reinterpret_cast<uint2 *>(p.emit_bf16 + grow * p.ld_emit + gcol) = make_uint2(pack_bf16x2(val.x, val.y), pack_bf16x2(val.z, val.w));
+                                float s1 = inb ? (val.x + val.y) + (val.z + val.w) : 0.f;
+                                float s2 = inb ? fmaf(val.x, val.x, fmaf(val.y, val.y, fmaf(val.z, val.z, val.w * val.w))) : 0.f;
+#pragma unroll
+                                for (int o = 1; o < 8; o <<= 1) {        // the 8 lanes that share rr hold the 32 columns of one row
+                                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                                }
+                                if (cc == i) ln_ps += s1, ln_pq += s2;
                             }
                         }
                         __syncwarp();
                     }
                     if (has_res && c == 0) load_res(1);
+                }
+                if (emit_ln && n0 < p.N) {
+                    const int64_t grow = m0 + 4 * cc + rr;
+                    if (grow < p.M && do_store)
+                        *reinterpret_cast<float2 *>(p.emit_stats + (grow * (p.N >> 6) + (n0 >> 6)) * 2) = make_float2(ln_ps, ln_pq);
                 }
             } else {
                 const int col0 = n0;
@@ -362,7 +422,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                         const int cb = col0 + hseg * 32;
-                        if (p.bias != nullptr) {
+                        if (ln_fold) {          // out = rstd (acc - mean colsum) + bias'
+                            const float nm = -ln_mean;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                if (cb + j < p.N) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + j));
+                                    const float4 cs = __ldg(reinterpret_cast<const float4 *>(p.ln_colsum + cb + j));
+                                    v[j] = fmaf(fmaf(nm, cs.x, v[j]), ln_rstd, b.x), v[j + 1] = fmaf(fmaf(nm, cs.y, v[j + 1]), ln_rstd, b.y);
+                                    v[j + 2] = fmaf(fmaf(nm, cs.z, v[j + 2]), ln_rstd, b.z), v[j + 3] = fmaf(fmaf(nm, cs.w, v[j + 3]), ln_rstd, b.w);
+                                }
+                            }
+                        } else if (p.bias != nullptr) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 if (cb + j < p.N) {
@@ -447,7 +518,15 @@ __global__ void __launch_bounds__(256) gemm_bf16_simple_kernel(const __nv_bfloat
         for (int j = 0; j < 4; ++j) {
             const int gn = n0 + tx * 4 + j;
             if (gn >= p.N) continue;
-            float v = acc[i][j] + (p.bias ? p.bias[gn] : 0.f);
+            float v = acc[i][j];
+            if (p.flags & SFB_GEMM_LN_FOLD) {
+                float s1 = 0.f, s2 = 0.f;
+                for (int t = 0; t < p.ln_parts; ++t) s1 += p.ln_stats[(static_cast<int64_t>(gm) * p.ln_parts + t) * 2], s2 += p.ln_stats[(static_cast<int64_t>(gm) * p.ln_parts + t) * 2 + 1];
+                const float mean = s1 / p.K;
+                const float rstd = rsqrtf(fmaxf(s2 / p.K - mean * mean, 0.f) + p.ln_eps);
+                v = (v - mean * p.ln_colsum[gn]) * rstd;
+            }
+            v += p.bias ? p.bias[gn] : 0.f;
             if (p.flags & SFB_GEMM_GELU) v = gelu_erf(v);
             if (p.flags & SFB_GEMM_RESIDUAL) v += p.residual[static_cast<int64_t>(gm) * p.ldr + gn];
             if (p.flags & SFB_GEMM_OUT_F32)
@@ -469,6 +548,13 @@ static int make_tmap(CUtensorMap *map, const void *base, int64_t rows, int64_t c
 
 extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const float *bias, const float *residual, int64_t ldr,
                              void *out, int64_t ldo, int M, int N, int K, int flags, int impl, void *stream) {
+    SFB_CHECK_ARG(!(flags & (SFB_GEMM_LN_FOLD | SFB_GEMM_EMIT_LN)), "sfb_gemm_bf16: the LayerNorm-fusion flags need sfb_gemm_bf16_ln");
+    return sfb_gemm_bf16_ln(A, lda, W, bias, residual, ldr, out, ldo, M, N, K, flags, impl, nullptr, 0, nullptr, 0.f, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const float *bias, const float *residual, int64_t ldr,
+                                void *out, int64_t ldo, int M, int N, int K, int flags, int impl, const float *ln_stats, int ln_parts,
+                                const float *ln_colsum, float ln_eps, float *emit_stats, void *emit_bf16, int64_t ld_emit, void *stream) {
     using namespace sfb;
     using namespace sfb::gemm;
     SFB_CHECK_ARG(A && W && out, "sfb_gemm_bf16: null pointer");
@@ -485,11 +571,25 @@ extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const fl
                       "sfb_gemm_bf16: residual must be non-null, 16-byte aligned, ldr %% 4 == 0");
     }
     SFB_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "sfb_gemm_bf16: bias must be 16-byte aligned");
+    if (flags & SFB_GEMM_LN_FOLD) {
+        SFB_CHECK_ARG(!(flags & SFB_GEMM_OUT_F32) || impl == 1, "sfb_gemm_bf16_ln: LN_FOLD writes bf16 (qkv / fc1 style consumers)");
+        SFB_CHECK_ARG(ln_stats && ln_colsum && bias && ln_parts > 0 && ln_eps >= 0.f, "sfb_gemm_bf16_ln: LN_FOLD needs ln_stats, ln_colsum, bias, ln_parts > 0");
+        SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(ln_stats) & 15) == 0 && (reinterpret_cast<uintptr_t>(ln_colsum) & 15) == 0,
+                      "sfb_gemm_bf16_ln: ln_stats / ln_colsum must be 16-byte aligned");
+    }
+    if (flags & SFB_GEMM_EMIT_LN) {
+        SFB_CHECK_ARG(impl != 1 && (flags & SFB_GEMM_OUT_F32), "sfb_gemm_bf16_ln: EMIT_LN belongs to the fp32-output (residual stream) epilogue of the tcgen05 kernel");
+        SFB_CHECK_ARG(emit_stats && emit_bf16 && N % 64 == 0 && ld_emit >= N && ld_emit % 4 == 0 && (reinterpret_cast<uintptr_t>(emit_bf16) & 7) == 0 &&
+                          (reinterpret_cast<uintptr_t>(emit_stats) & 7) == 0,
+                      "sfb_gemm_bf16_ln: EMIT_LN needs emit_stats (M x N/64 x 2 floats), emit_bf16 (row stride ld_emit >= N, %% 4), N %% 64 == 0");
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
     EpiParams p;
     p.bias = bias, p.residual = residual, p.ldr = ldr, p.out = out, p.ldo = ldo;
     p.M = M, p.N = N, p.K = K, p.flags = flags;
+    p.ln_stats = ln_stats, p.ln_colsum = ln_colsum, p.ln_parts = ln_parts, p.ln_eps = ln_eps;
+    p.emit_stats = emit_stats, p.emit_bf16 = reinterpret_cast<__nv_bfloat16 *>(emit_bf16), p.ld_emit = ld_emit;
     p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
     static const int order_env = getenv("SFB_GEMM_ORDER") ? atoi(getenv("SFB_GEMM_ORDER")) : 0;
@@ -504,60 +604,54 @@ extern "C" int sfb_gemm_bf16(const void *A, int64_t lda, const void *W, const fl
         SFB_CHECK_LAUNCH();
         return SFB_OK;
     }
-    SFB_CHECK_ARG(impl == 0 || impl == 2 || impl == 3 || impl == 4,
-                  "sfb_gemm_bf16: unknown impl %d (0 auto, 1 CUDA-core check, 2 single-CTA, 3 CTA-pair, 4 two pairs + W multicast)", impl);
-    // CTA pairs (256-row tiles) unless the problem has at most one 128-row block; clusters of two pairs when asked for
-    static const int cl_env = getenv("SFB_GEMM_CL") ? atoi(getenv("SFB_GEMM_CL")) : 2;
-    const int cg = impl == 2 ? 1 : (impl == 3 || impl == 4) ? 2 : (M > BLOCK_M ? 2 : 1);
-    const int cl = cg == 1 ? 1 : impl == 4 ? 4 : impl == 3 ? 2 : (cl_env == 4 && M > 2 * BLOCK_M ? 4 : 2);
+    SFB_CHECK_ARG(impl == 0 || impl == 2 || impl == 3, "sfb_gemm_bf16: unknown impl %d (0 auto, 1 CUDA-core check, 2 single-CTA, 3 CTA-pair)", impl);
+    // CTA pairs (256-row tiles) unless the problem has at most one 128-row block
+    const int cg = impl == 2 ? 1 : impl == 3 ? 2 : (M > BLOCK_M ? 2 : 1);
+    const int epi = (flags & SFB_GEMM_OUT_F32) ? ((flags & SFB_GEMM_EMIT_LN) ? EPI_F32_LN : EPI_F32) : ((flags & SFB_GEMM_LN_FOLD) ? EPI_BF16_LN : EPI_BF16);
 
     CUtensorMap tmap_a, tmap_w;
     int rc = make_tmap(&tmap_a, A, M, K, lda, BLOCK_M);
     if (rc != SFB_OK) return rc;
-    rc = make_tmap(&tmap_w, W, N, K, K, BLOCK_N / cl);           // rows of W fetched by one CTA per k-block
+    rc = make_tmap(&tmap_w, W, N, K, K, BLOCK_N / cg);           // rows of W fetched by one CTA per k-block
     if (rc != SFB_OK) return rc;
 
-    if (cg == 1) {
-        static PerDeviceOnce attr_once;
-        if (attr_once.first())
-            SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
-        const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-        const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-        gemm_bf16_tcgen05_kernel<1, 1><<<grid, kThreads, Cfg<1>::SMEM_BYTES, st>>>(tmap_a, tmap_w, p);
-        SFB_CHECK_LAUNCH();
-        return SFB_OK;
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
+#define SFB_GEMM_ATTR(CGV, EPIV) \
+    SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<CGV, EPIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CGV>::SMEM_BYTES))
+        SFB_GEMM_ATTR(1, EPI_BF16); SFB_GEMM_ATTR(1, EPI_BF16_LN); SFB_GEMM_ATTR(1, EPI_F32); SFB_GEMM_ATTR(1, EPI_F32_LN);
+        SFB_GEMM_ATTR(2, EPI_BF16); SFB_GEMM_ATTR(2, EPI_BF16_LN); SFB_GEMM_ATTR(2, EPI_F32); SFB_GEMM_ATTR(2, EPI_F32_LN);
+#undef SFB_GEMM_ATTR
     }
-    static PerDeviceOnce attr_once2;
-    if (attr_once2.first()) {
-        SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
-        SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
-    }
-    p.num_m_blocks = (M + cl * BLOCK_M - 1) / (cl * BLOCK_M);           // 256-row (pair) or 512-row (two pairs) tiles
+    p.num_m_blocks = (M + cg * BLOCK_M - 1) / (cg * BLOCK_M);           // 128-row (single CTA) or 256-row (pair) tiles
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = cg == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cl, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = cg, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    int max_clusters = num_sms() / cl;
-    if (cl == 4) {      // 4-CTA clusters do not tile every GPC: ask how many can be co-resident
-        static int cached = 0;
-        if (cached == 0) {
-            cfg.gridDim = dim3(cl * (num_sms() / cl));
-            int n = 0;
-            SFB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_bf16_tcgen05_kernel<2, 4>, &cfg));
-            cached = n > 0 ? n : 1;
-        }
-        max_clusters = cached < max_clusters ? cached : max_clusters;
-    }
+    const int max_clusters = num_sms() / cg;
     const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-    cfg.gridDim = dim3(cl * clusters);
-    if (cl == 4)
-        SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2, 4>, tmap_a, tmap_w, p));
-    else
-        SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2, 2>, tmap_a, tmap_w, p));
+    cfg.gridDim = dim3(cg * clusters);
+#define SFB_GEMM_LAUNCH(CGV, EPIV) SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<CGV, EPIV>, tmap_a, tmap_w, p))
+    if (cg == 2) {
+        switch (epi) {
+            case EPI_BF16: SFB_GEMM_LAUNCH(2, EPI_BF16); break;
+            case EPI_BF16_LN: SFB_GEMM_LAUNCH(2, EPI_BF16_LN); break;
+            case EPI_F32: SFB_GEMM_LAUNCH(2, EPI_F32); break;
+            default: SFB_GEMM_LAUNCH(2, EPI_F32_LN); break;
+        }
+    } else {
+        switch (epi) {
+            case EPI_BF16: SFB_GEMM_LAUNCH(1, EPI_BF16); break;
+            case EPI_BF16_LN: SFB_GEMM_LAUNCH(1, EPI_BF16_LN); break;
+            case EPI_F32: SFB_GEMM_LAUNCH(1, EPI_F32); break;
+            default: SFB_GEMM_LAUNCH(1, EPI_F32_LN); break;
+        }
+    }
+#undef SFB_GEMM_LAUNCH
     return SFB_OK;
 }

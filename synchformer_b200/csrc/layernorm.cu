@@ -57,7 +57,37 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(const float *__restri
     }
 }
 
+// LN_FOLD inputs for rows that no EMIT_LN epilogue produced: bf16 copy + (sum, sum of squares) per row; same data movement as a LayerNorm
+__global__ void __launch_bounds__(256) rowstats_cast_kernel(const float *__restrict__ x, int64_t ldx, __nv_bfloat16 *__restrict__ xb,
+                                                            float *__restrict__ stats, int rows) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= rows) return;
+    const float4 *xp = reinterpret_cast<const float4 *>(x + static_cast<int64_t>(r) * ldx);
+    uint2 *op = reinterpret_cast<uint2 *>(xb + static_cast<int64_t>(r) * kD);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const float4 v = __ldg(xp + lane + 32 * j);
+        s1 += (v.x + v.y) + (v.z + v.w);
+        s2 += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+        op[lane + 32 * j] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    s1 = warp_sum(s1), s2 = warp_sum(s2);
+    if (lane == 0) *reinterpret_cast<float2 *>(stats + static_cast<int64_t>(r) * 2) = make_float2(s1, s2);
+}
+
 }  // namespace sfb
+
+extern "C" int sfb_rowstats_cast(const float *x, int64_t ldx, void *xb, float *stats, int rows, void *stream) {
+    using namespace sfb;
+    SFB_CHECK_ARG(x && xb && stats && rows > 0, "sfb_rowstats_cast: bad arguments");
+    SFB_CHECK_ARG(ldx % 4 == 0 && ldx >= kD && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(xb) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(stats) & 7) == 0, "sfb_rowstats_cast: alignment");
+    rowstats_cast_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, reinterpret_cast<__nv_bfloat16 *>(xb), stats, rows);
+    SFB_CHECK_LAUNCH();
+    return SFB_OK;
+}
 
 extern "C" int sfb_layernorm(const float *x, int64_t ldx, void *out, int64_t ldo, int out_f32, const float *gamma, const float *beta,
                              float eps, const float *gamma2, const float *beta2, float eps2, int rows, int group, int group_stride,

@@ -165,7 +165,7 @@ def _cls_aggregator(P, W, prefix: str, kv_src: torch.Tensor, n_groups_outer: int
     # the CLS token is a learned constant -> its norm1 / q / k / v rows are computed once per call (M = 1 GEMM)
     cls_ln = ops.layernorm(P[prefix + 'cls_token'].view(1, D), P[prefix + 'norm1.weight'], P[prefix + 'norm1.bias'], EPS_V)
     cls_qkv = ops.gemm(cls_ln, W[prefix + 'in_w'], P[prefix + 'self_attn.in_proj_bias'])              # (1, 2304) bf16
-    ao = torch.empty((G, D), device=dev, dtype=torch.bfloat16)
+    ao = ops.empty_bf16((G, D), dev)
     ops.attention(cls_qkv, kv, kv[:, D:], ao, q_strides=(0, 0, 0),
                   kv_strides=(kv_outer_rows * 2 * D, kv_inner_rows * 2 * D, kv_row_rows * 2 * D),
                   o_strides=(n_inner * D, D, D), n_outer=n_groups_outer, n_inner=n_inner, n_heads=12, head_dim=64, Lq=1, Lk=Lk,
@@ -204,6 +204,10 @@ class MotionFormer(_KernelModule):
         self.extract_features, self.factorize_space_time, self.add_global_repr = True, True, False
         self.embed_dim, self.num_heads = D, 12
         self.max_segments_per_pass = 512
+        # LayerNorm fused into the GEMMs on either side of it (csrc/gemm_tcgen05.cu: EMIT_LN / LN_FOLD) instead of 36 LayerNorm launches per
+        # pass.  Opt-in (SFB_LN_FUSED=1): measured on the B200 (profiles/r2_ln_fusion_ab.txt) the fused schedule removes 20 ms of LayerNorm
+        # passes per 64-clip step but adds 34 ms to the GEMM epilogues, which are the bottleneck of those kernels already.
+        self.fuse_layernorm = os.environ.get('SFB_LN_FUSED', '0') == '1'
         schema = {k[len('vfeat_extractor.'):]: v for k, v in state_dict_schema().items() if k.startswith('vfeat_extractor.')}
         _build_tree(self, schema)
         _init_reference_like(self)
@@ -217,6 +221,15 @@ class MotionFormer(_KernelModule):
             b = f'blocks.{i}.'
             for n in ('attn.qkv', 'attn.proj', 'timeattn.qkv', 'timeattn.proj', 'mlp.fc1', 'mlp.fc2'):
                 W[b + n] = self._bf16(P[b + n + '.weight'])
+            # LayerNorm folded into the Linear that consumes it (vit_helper.py:366-375: norm3 -> timeattn.qkv, norm1 -> attn.qkv, norm2 -> mlp.fc1):
+            #   LN(x) W^T + b = rstd (x (gamma . W)^T - mean colsum) + (b + W beta)
+            for norm, lin in (('norm3', 'timeattn.qkv'), ('norm1', 'attn.qkv'), ('norm2', 'mlp.fc1')):
+                w0, b0 = P[b + lin + '.weight'], P[b + lin + '.bias']
+                gamma, beta = P[b + norm + '.weight'], P[b + norm + '.bias']
+                wf = self._bf16(w0 * gamma.unsqueeze(0))
+                W[b + lin + '.fold_w'] = wf
+                W[b + lin + '.fold_cs'] = wf.float().sum(dim=1).contiguous()          # sums of the weights AS THE TENSOR CORES SEE THEM
+                W[b + lin + '.fold_b'] = (b0 + w0 @ beta).contiguous()
         _pack_aggregator(P, 'spatial_attn_agg.', W, self._bf16)
         return W
 
@@ -250,11 +263,29 @@ class MotionFormer(_KernelModule):
         del a, patch
         self._tap('v_embed', x, V_TOK)
         M = n * V_TOK
-        ln = torch.empty((M, D), device=dev, dtype=torch.bfloat16)
-        qkv = torch.empty((M, 3 * D), device=dev, dtype=torch.bfloat16)
-        att = torch.empty((M, D), device=dev, dtype=torch.bfloat16)
-        hid = torch.empty((M, 4 * D), device=dev, dtype=torch.bfloat16)
-        for i in range(12):                                                                    # DividedSpaceTimeBlock vit_helper.py:364-376
+        ln, qkv, att, hid = (ops.empty_bf16((M, w * D), dev) for w in (1, 3, 1, 4))
+        fused = self.fuse_layernorm and ops.GEMM_IMPL != 1          # the CUDA-core bring-up GEMM has no EMIT_LN epilogue
+        if fused:
+            # No LayerNorm pass inside the blocks: every residual GEMM (proj / fc2) leaves a bf16 copy of the stream in `ln` plus per-row
+            # partial sums in `st`, and the next qkv / fc1 GEMM normalises in its epilogue (folded gamma / beta).
+            st0 = torch.empty((M, 1, 2), device=dev, dtype=torch.float32)
+            st = torch.empty((M, D // 64, 2), device=dev, dtype=torch.float32)
+            ops.rowstats_cast(x, ln, st0)
+            cur = st0
+            for i in range(12):                                                                # DividedSpaceTimeBlock vit_helper.py:364-376
+                b = f'blocks.{i}.'
+                ops.gemm(ln, W[b + 'timeattn.qkv.fold_w'], W[b + 'timeattn.qkv.fold_b'], out=qkv, ln_fold=(cur, W[b + 'timeattn.qkv.fold_cs'], EPS_V))
+                self._divided_attention(qkv, att, n, 'time')
+                ops.gemm(att, W[b + 'timeattn.proj'], P[b + 'timeattn.proj.bias'], out=x, residual=x, out_f32=True, emit_ln=(ln, st))
+                cur = st
+                ops.gemm(ln, W[b + 'attn.qkv.fold_w'], W[b + 'attn.qkv.fold_b'], out=qkv, ln_fold=(st, W[b + 'attn.qkv.fold_cs'], EPS_V))
+                self._divided_attention(qkv, att, n, 'space')
+                ops.gemm(att, W[b + 'attn.proj'], P[b + 'attn.proj.bias'], out=x, residual=x, out_f32=True, emit_ln=(ln, st))
+                ops.gemm(ln, W[b + 'mlp.fc1.fold_w'], W[b + 'mlp.fc1.fold_b'], out=hid, gelu=True, ln_fold=(st, W[b + 'mlp.fc1.fold_cs'], EPS_V))
+                ops.gemm(hid, W[b + 'mlp.fc2'], P[b + 'mlp.fc2.bias'], out=x, residual=x, out_f32=True, emit_ln=(ln, st) if i < 11 else None)
+                if i in (0, 11):
+                    self._tap(f'v_block{i}', x, V_TOK)
+        for i in range(0 if fused else 12):                                                    # one LayerNorm launch per norm (default)
             b = f'blocks.{i}.'
             ops.layernorm(x, P[b + 'norm3.weight'], P[b + 'norm3.bias'], EPS_V, out=ln)
             ops.gemm(ln, W[b + 'timeattn.qkv'], P[b + 'timeattn.qkv.bias'], out=qkv)

@@ -10,7 +10,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import AttnDesc, SFB_GEMM_GELU, SFB_GEMM_OUT_F32, SFB_GEMM_RESIDUAL, check
+from ._lib import AttnDesc, SFB_GEMM_EMIT_LN, SFB_GEMM_GELU, SFB_GEMM_LN_FOLD, SFB_GEMM_OUT_F32, SFB_GEMM_RESIDUAL, check
 
 D = 768
 
@@ -54,9 +54,15 @@ def device_check():
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None, *, gelu: bool = False,
-         residual: Optional[torch.Tensor] = None, out_f32: bool = False, impl: Optional[int] = None) -> torch.Tensor:
+         residual: Optional[torch.Tensor] = None, out_f32: bool = False, impl: Optional[int] = None, ln_fold=None, emit_ln=None) -> torch.Tensor:
     """out = epi(a @ w.T + bias).  a (M, K) bf16 (row stride may exceed K), w (N, K) bf16 contiguous, bias (N,) fp32,
-    residual (M, N) or (1, N) fp32 (broadcast)."""
+    residual (M, N) or (1, N) fp32 (broadcast).
+
+    LayerNorm fusion (see sfb_gemm_bf16_ln in the header):
+      ln_fold = (stats (M, parts, 2) fp32, colsum (N,) fp32, eps): `a` holds UN-normalised rows, `w` / `bias` are the folded weights; the
+                epilogue applies rstd (acc - mean colsum) + bias.  bf16 output.
+      emit_ln = (xb (M, N) bf16, stats (M, N // 64, 2) fp32): a residual GEMM also writes the bf16 copy of its fp32 output and the per-row
+                partial (sum, sum of squares) - the ln_fold inputs of the next Linear."""
     require_cuda(a, 'a')
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.is_contiguous()
@@ -74,10 +80,48 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Op
         ldr = 0 if residual.numel() == N else residual.stride(0)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
-    check(_lib.load().sfb_gemm_bf16(_p(a), a.stride(0), _p(w), _p(bias), _p(residual), ldr, _p(out), out.stride(0), M, N, K, flags,
-                                    GEMM_IMPL if impl is None else impl, _stream(a)), 'sfb_gemm_bf16')
+    impl = GEMM_IMPL if impl is None else impl
+    if ln_fold is None and emit_ln is None:
+        check(_lib.load().sfb_gemm_bf16(_p(a), a.stride(0), _p(w), _p(bias), _p(residual), ldr, _p(out), out.stride(0), M, N, K, flags,
+                                        impl, _stream(a)), 'sfb_gemm_bf16')
+        _count()
+        return out
+    stats_in = colsum = stats_out = xb = None
+    parts, eps, ld_emit = 0, 0.0, 0
+    if ln_fold is not None:
+        stats_in, colsum, eps = ln_fold
+        assert stats_in.dtype == torch.float32 and stats_in.is_contiguous() and stats_in.dim() == 3 and stats_in.shape[0] >= M and stats_in.shape[2] == 2
+        assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == N and bias is not None and not out_f32
+        parts = stats_in.shape[1]
+        flags |= SFB_GEMM_LN_FOLD
+    if emit_ln is not None:
+        xb, stats_out = emit_ln
+        assert out_f32 and N % 64 == 0 and xb.dtype == torch.bfloat16 and xb.shape == (M, N) and xb.stride(1) == 1
+        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and tuple(stats_out.shape) == (M, N // 64, 2)
+        ld_emit = xb.stride(0)
+        flags |= SFB_GEMM_EMIT_LN
+        if impl == 1:
+            raise _lib.SfbError('emit_ln is not available on the CUDA-core cross-check kernel')
+    check(_lib.load().sfb_gemm_bf16_ln(_p(a), a.stride(0), _p(w), _p(bias), _p(residual), ldr, _p(out), out.stride(0), M, N, K, flags, impl,
+                                       _p(stats_in), parts, _p(colsum), float(eps), _p(stats_out), _p(xb), ld_emit, _stream(a)), 'sfb_gemm_bf16_ln')
     _count()
     return out
+
+
+def rowstats_cast(x: torch.Tensor, xb: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None):
+    """x (R, 768) fp32 -> (xb (R, 768) bf16, stats (R, 1, 2) fp32 = per-row (sum, sum of squares)): the `ln_fold` inputs of gemm() for rows
+    that did not come out of an `emit_ln` GEMM."""
+    require_cuda(x, 'x')
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == D and x.stride(1) == 1
+    R = x.shape[0]
+    if xb is None:
+        xb = torch.empty((R, D), device=x.device, dtype=torch.bfloat16)
+    if stats is None:
+        stats = torch.empty((R, 1, 2), device=x.device, dtype=torch.float32)
+    assert xb.dtype == torch.bfloat16 and xb.is_contiguous() and xb.shape == (R, D) and stats.is_contiguous() and tuple(stats.shape) == (R, 1, 2)
+    check(_lib.load().sfb_rowstats_cast(_p(x), x.stride(0), _p(xb), _p(stats), R, _stream(x)), 'sfb_rowstats_cast')
+    _count()
+    return xb, stats
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None, *,

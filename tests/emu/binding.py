@@ -20,7 +20,7 @@ EMULATED = ('sfb_dropout', 'sfb_gelu_fwd', 'sfb_gelu_bwd', 'sfb_transpose_bf16',
             'sfb_mean_tokens', 'sfb_mean_tokens_bwd', 'sfb_l2_normalize', 'sfb_l2_normalize_bwd', 'sfb_contrastive_loss', 'sfb_contrastive_loss_bwd',
             # verified on the B200 in round 1 (no inline PTX): emulating them checks the emulator against kernels known to be right
             'sfb_layernorm', 'sfb_im2col_video', 'sfb_im2col_video_clip', 'sfb_video_tokens', 'sfb_im2col_ast', 'sfb_ast_tokens', 'sfb_sync_tokens',
-            'sfb_sync_head', 'sfb_cast_f32_bf16',
+            'sfb_sync_head', 'sfb_cast_f32_bf16', 'sfb_rowstats_cast',
             # the mma.sync / ldmatrix / cp.async attention kernels (their PTX is emulated instruction by instruction)
             'sfb_attention', 'sfb_attention_extra_supported', 'sfb_attention_merge_partials')
 STAND_INS = ('require_cuda', 'gemm')          # the tcgen05 GEMM is not emulated: torch stand-in (hardware-verified in round 1)

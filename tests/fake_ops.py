@@ -37,19 +37,43 @@ def cast_bf16(x):
     return _r(x.float())
 
 
-def gemm(a, w, bias, out=None, *, gelu=False, residual=None, out_f32=False, impl=None):
+def gemm(a, w, bias, out=None, *, gelu=False, residual=None, out_f32=False, impl=None, ln_fold=None, emit_ln=None):
+    """restates the sfb_gemm_bf16 / sfb_gemm_bf16_ln contract (include/synchformer_b200.h)"""
     y = a.float() @ w.float().t()
+    if ln_fold is not None:                      # rstd (acc - mean colsum) + bias from the partial (sum, sum of squares) of the A rows
+        stats, colsum, eps = ln_fold
+        K = a.shape[1]
+        s1, s2 = stats[:a.shape[0], :, 0].sum(1, keepdim=True), stats[:a.shape[0], :, 1].sum(1, keepdim=True)
+        mean = s1 / K
+        rstd = torch.rsqrt((s2 / K - mean * mean).clamp_min(0.0) + eps)
+        y = (y - mean * colsum.unsqueeze(0)) * rstd
     if bias is not None:
         y = y + bias
     if gelu:
         y = F.gelu(y)
     if residual is not None:
         y = y + residual.reshape(-1, y.shape[1])
+    if emit_ln is not None:
+        xb, stats_out = emit_ln
+        xb.copy_(_r(y))
+        g = y.reshape(y.shape[0], y.shape[1] // 64, 64)
+        stats_out.copy_(torch.stack([g.sum(-1), (g * g).sum(-1)], dim=-1))
     y = y if out_f32 else _r(y)
     if out is not None:
         out.copy_(y)
         return out
     return y
+
+
+def rowstats_cast(x, xb=None, stats=None):
+    x = x.float()
+    if xb is None:
+        xb = empty_bf16(x.shape, x.device)
+    if stats is None:
+        stats = torch.empty((x.shape[0], 1, 2))
+    xb.copy_(_r(x))
+    stats.copy_(torch.stack([x.sum(-1, keepdim=True), (x * x).sum(-1, keepdim=True)], dim=-1))
+    return xb, stats
 
 
 def layernorm(x, gamma, beta, eps, out=None, *, rows=None, group=None, group_stride=None, offset=0, gamma2=None, beta2=None, eps2=0.0,
@@ -336,7 +360,7 @@ def contrastive_loss_bwd(vn, an, vn_all, an_all, G, scale, upstream, dscale):
 
 CONTRASTIVE = ('mean_tokens', 'mean_tokens_bwd', 'l2_normalize', 'l2_normalize_bwd', 'contrastive_loss', 'contrastive_loss_bwd')
 N1_BWD = ('attention_bwd', 'attention_bwd_global_query', 'droppath', 'gather_rows_bf16', 'empty_bf16')
-ENCODER_FWD = ('im2col_video', 'video_tokens', 'im2col_ast', 'ast_tokens', 'attention')
+ENCODER_FWD = ('im2col_video', 'video_tokens', 'im2col_ast', 'ast_tokens', 'attention', 'rowstats_cast')
 
 ALL = ('require_cuda', 'cast_bf16', 'gemm', 'layernorm', 'sync_tokens', 'sync_head', 'dropout', 'gelu_fwd', 'gelu_bwd',
        'transpose_bf16', 'colsum', 'layernorm_bwd', 'attention_train_fwd', 'attention_train_bwd', 'sync_head_bwd')

@@ -25,7 +25,7 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(2, id='tc1cta'), pytest.param(3, id='tcpair'), pytest.param(4, id='tcquad'), pytest.param(1, id='simple')])
+@pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(2, id='tc1cta'), pytest.param(3, id='tcpair'), pytest.param(1, id='simple')])
 @pytest.mark.parametrize('M,N,K', GEMM_SHAPES)
 def test_gemm_bias(cuda_device, impl, M, N, K):
     from synchformer_b200 import ops
@@ -73,6 +73,62 @@ def test_gemm_epilogues(cuda_device, impl):
     assert rel_l2(dst[:, N:].float(), wide[:, K:2 * K].float() @ w.float().T + b) < 4e-3
     assert float(dst[:, :N].abs().max()) == 0.0
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('impl', [pytest.param(0, id='auto'), pytest.param(2, id='tc1cta'), pytest.param(3, id='tcpair')])
+@pytest.mark.parametrize('M,N,gelu', [(1000, 2304, False), (517, 3072, True), (100, 1536, False), (1569 * 3, 768, False)])
+def test_gemm_layernorm_fusion(cuda_device, impl, M, N, gelu):
+    """sfb_gemm_bf16_ln: a residual GEMM that EMITs the bf16 copy + row statistics of its fp32 output, feeding a GEMM that applies the
+    LayerNorm in its epilogue through folded weights (LN_FOLD) - against the definitions in the header, and against the unfused pair
+    LayerNorm kernel + plain GEMM (vit_helper.py:366-375: x += proj(...); y = Linear(norm(x)))."""
+    from synchformer_b200 import ops
+    D = 768
+    g = torch.Generator(device='cuda').manual_seed(M + N)
+    att = _bf(torch.randn(M, D, device='cuda', generator=g))
+    wp = _bf(torch.randn(D, D, device='cuda', generator=g) * 0.04)
+    bp = torch.randn(D, device='cuda', generator=g) * 0.1
+    x0 = torch.randn(M, D, device='cuda', generator=g) * 1.5 + 0.3                        # residual stream with a non-zero mean
+    x0[:, 5] += 20.0                                                                       # and one outlier channel
+    gamma, beta = torch.rand(D, device='cuda', generator=g) + 0.5, torch.randn(D, device='cuda', generator=g) * 0.2
+    w0 = torch.randn(N, D, device='cuda', generator=g) * 0.03
+    b0 = torch.randn(N, device='cuda', generator=g) * 0.1
+    eps = 1e-6
+    # producer: x = x0 + att wp^T + bp, plus bf16 copy and per-row (sum, sum of squares) per 64-column group
+    xb, st = torch.empty(M, D, device='cuda', dtype=torch.bfloat16), torch.empty(M, D // 64, 2, device='cuda')
+    x = ops.gemm(att, wp, bp, residual=x0, out_f32=True, emit_ln=(xb, st), impl=impl)
+    x_plain = ops.gemm(att, wp, bp, residual=x0, out_f32=True, impl=impl)
+    torch.cuda.synchronize()
+    assert torch.equal(x, x_plain)                                                         # the fp32 result is unchanged by the emission
+    assert torch.equal(xb, x.to(torch.bfloat16))                                           # bit-exact copy
+    grp = x.double().view(M, D // 64, 64)
+    ref_st = torch.stack([grp.sum(-1), (grp * grp).sum(-1)], dim=-1)
+    assert (st.double() - ref_st).abs().max() <= 2e-5 * ref_st.abs().max()
+    # consumer with folded weights
+    wf = _bf(w0 * gamma.unsqueeze(0))
+    cs = wf.float().sum(1).contiguous()
+    bf = (b0 + w0 @ beta).contiguous()
+    y = ops.gemm(xb, wf, bf, gelu=gelu, ln_fold=(st, cs, eps), impl=impl)
+    torch.cuda.synchronize()
+    mean = x.double().mean(-1, keepdim=True)
+    rstd = torch.rsqrt(x.double().var(-1, unbiased=False, keepdim=True) + eps)
+    ref = ((xb.double() - mean) * rstd) @ wf.double().T + bf.double()                      # the header's definition
+    ref = torch.nn.functional.gelu(ref) if gelu else ref
+    assert y.dtype == torch.bfloat16 and rel_l2(y.float(), ref) < 4e-3
+    # the CUDA-core cross-check kernel implements the same LN_FOLD epilogue
+    y1 = ops.gemm(xb, wf, bf, gelu=gelu, ln_fold=(st, cs, eps), impl=1)
+    assert rel_l2(y1.float(), ref) < 4e-3
+    # and the fused pair equals the unfused pair (LayerNorm kernel + plain GEMM on unfolded weights) to bf16 rounding
+    ln = ops.layernorm(x, gamma, beta, eps)
+    y_unfused = ops.gemm(ln, _bf(w0), b0, gelu=gelu, impl=impl)
+    exact = torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), eps) @ w0.double().T + b0.double()
+    exact = torch.nn.functional.gelu(exact) if gelu else exact
+    e_f, e_u = rel_l2(y.float(), exact), rel_l2(y_unfused.float(), exact)
+    assert e_f < 8e-3 and e_f < 1.5 * e_u + 1e-3, (e_f, e_u)
+    # rows that no EMIT_LN epilogue produced: sfb_rowstats_cast (one partial per row)
+    xb1, st1 = ops.rowstats_cast(x)
+    assert torch.equal(xb1, xb)
+    y2 = ops.gemm(xb1, wf, bf, gelu=gelu, ln_fold=(st1, cs, eps), impl=impl)
+    assert rel_l2(y2.float(), ref) < 4e-3
 
 
 def test_gemm_full_size_linearity_property(cuda_device):

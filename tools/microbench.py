@@ -53,6 +53,19 @@ def main():
             # it is a LOWER bound on what a library path would need for the fused op.  Measurement aid only, never on the product path.
             cub = timeit(lambda: torch.nn.functional.linear(a, W, bias.bfloat16()))
             res['gemm ' + name].update({'cublas_ms': cub, 'cublas_TFLOPs': fl / cub / 1e9})
+    # LayerNorm-fused variants (EMIT_LN producer, LN_FOLD consumer) next to the unfused pair they replace
+    xb = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    st = torch.empty(M, D // 64, 2, device=dev)
+    for name, a, N, K, kw in [('proj 768->768 +res f32 +emit_ln', att, 768, 768, dict(out=x, residual=x, out_f32=True, emit_ln=(xb, st))),
+                              ('fc2 3072->768 +res f32 +emit_ln', hid, 768, 3072, dict(out=x, residual=x, out_f32=True, emit_ln=(xb, st)))]:
+        W, bias = w(N, K)
+        ms = timeit(lambda: ops.gemm(a, W, bias, **kw))
+        res['gemm ' + name] = {'ms': ms, 'TFLOPs': 2.0 * M * N * K / ms / 1e9}
+    for name, N, kw in [('qkv 768->2304 ln_fold', 2304, dict(out=qkv)), ('fc1 768->3072 gelu ln_fold', 3072, dict(out=hid, gelu=True))]:
+        W, bias = w(N, 768)
+        cs = W.float().sum(1).contiguous()
+        ms = timeit(lambda: ops.gemm(xb, W, bias, ln_fold=(st, cs, 1e-6), **kw))
+        res['gemm ' + name] = {'ms': ms, 'TFLOPs': 2.0 * M * N * 768 / ms / 1e9}
     if os.environ.get('SFB_MB_GEMM_ONLY') == '1':
         for k, v in res.items():
             print(f'{k:36s} ' + '  '.join(f'{kk}={vv:9.3f}' for kk, vv in v.items()))
