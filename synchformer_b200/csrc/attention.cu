@@ -636,7 +636,6 @@ extern "C" int sfb_attention_extra_supported(const sfb_attn_desc *desc) {
     if (desc == nullptr || desc->impl != 0 || desc->head_dim != 64 || !sfb_attn_aligned16(desc)) return 0;
     if (sfb_time_extra_supported(desc)) return 1;
     if (getenv("SFB_ATTN_TC") && atoi(getenv("SFB_ATTN_TC")) == 0) return 0;
-    if (getenv("SFB_ATTN_TC_VARIANT") && atoi(getenv("SFB_ATTN_TC_VARIANT")) != 1) return 0;
     if ((reinterpret_cast<uintptr_t>(desc->q_extra) & 15) != 0 || desc->q_extra_outer % 8 != 0) return 0;
     Desc d = {};
     d.Lq = desc->Lq, d.Lk = desc->Lk, d.has_prefix = desc->k_prefix != nullptr;

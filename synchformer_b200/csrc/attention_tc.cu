@@ -11,19 +11,20 @@
 //   warp 8      MMA issuer  S_t = Q_t K^T   (2 row tiles t of 128 queries; 4 x tcgen05.mma M128 N208 K16, operands from smem)
 //                           O_t = P_t V     (13 x tcgen05.mma M128 N64 K16, A = P_t read from TMEM, B = V as an MN-major operand:
 //                           the [key][64 dims] rows are used as they are, no transpose)
-//   warps 0-7   softmax     thread = query row (TMEM lane).  ONE pass over the fp32 scores with software-pipelined tcgen05.ld (exp2 / row
-//                           sum), P written back over S as packed bf16 with tcgen05.st, then the O epilogue: tcgen05.ld, 1/sum, bf16,
-//                           one 128-byte row store per thread.  The kernel is bound by TMEM READ bandwidth (the round-1 version read
-//                           S twice - row max, then exp - and its 7 650 clocks per problem were exactly its 490 KB of tcgen05.ld at
-//                           64 B/clk), so the softmax reference value is not the row max but the Cauchy-Schwarz bound
-//                               m_i = |q_i| max_j |k_j| scale   >=  max_j s_ij
-//                           computed from the operand tiles in shared memory while the tensor core forms S.  softmax is invariant to
-//                           the reference value; bf16 / fp32 keep full relative precision for the (smaller) probabilities; a row whose
-//                           sum underflows (bound looser than ~2^100, never seen with LayerNorm-fed projections) is redone with the
-//                           exact two-pass scheme by its warp.
+//   warps 0-7   softmax     thread = query row (TMEM lane).  Two passes over the fp32 scores with software-pipelined tcgen05.ld
+//                           (row max, then exp2 / row sum), P written back over S as packed bf16 with tcgen05.st, then the O epilogue:
+//                           tcgen05.ld, 1/sum, bf16, one 128-byte row store per thread.
 // TMEM (512 columns): tile t owns columns [256t, 256t+208): S fp32 there; P (bf16 pairs) re-uses columns [0,104) of the same
 // range as the softmax consumes S; O accumulates in columns [128,192) once S is dead.
 // Nothing touches HBM between the qkv activations and the attention output.
+//
+// What bounds it (round 2, clock64 phase stamps of one CTA, tools/attn_modes.py): a problem takes ~9 600 clocks = S MMAs 1 450 (4
+// instructions, ~420 clocks of tensor work: the rest is issue -> commit -> waiter latency) -> row-max pass 850 -> exp2 pass 3 400 (the two
+// tiles' warps share the XU pipe) -> P V 1 600 (13 small M128 N64 K16 instructions at ~120 clocks each) -> O read / barrier hops.  Tried and
+// measured, not adopted: a single-pass softmax whose reference value is the Cauchy-Schwarz bound |q| max|k| scale (the max pass is only 8 %
+// of the time; computing the norms from shared memory plus a named barrier cost 30 %), and a software-pipelined issue order
+// S(0,i) PV(1,i-1) S(1,i) PV(0,i) (the in-order tensor pipe re-locks the two tiles; no gain).  The next step is more independent items
+// in flight per SM (cta_group::2 pairs: one 128-row tile per CTA, two problems in the 512 TMEM columns).
 #include <stdlib.h>
 #include <string.h>
 
@@ -81,7 +82,6 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     // barriers: full[2] empty[2] | s_ready[2] p_ready[2] o_ready[2] tmem_free[2]
     __shared__ __align__(8) uint64_t bars[12];
     __shared__ uint32_t tmem_slot;
-    __shared__ float kmax_s[2][kSoftmaxWarps];      // per problem parity: max_j |k_j|^2 of each softmax warp's key rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_g = smem_raw + (base - smem_u32(smem_raw));
@@ -361,200 +361,6 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------------
-// Variant B (kept for A/B measurements, SFB_ATTN_TC_VARIANT=2; measured slower than the persistent kernel): one CTA per problem, TWO CTAs resident per SM (84 KB of shared memory, 256 TMEM columns each).  A problem is a serial
-// chain (load -> S -> softmax -> P V -> epilogue, twice: one 128-row tile at a time); a second resident CTA fills the bubbles of
-// the first, the same way two CTAs per SM paid off for the time-attention kernel.  Warps 0-3 softmax + epilogue,
-// warp 4 MMA issuer, warp 5 producer (TMA boxes + CLS row).  Requires the regular (TMA) layout.
-constexpr int kThreadsTc2 = 256;   // 8 warps (warps 6, 7 idle): register allocation is per 4 warps, so 2 CTAs per SM need <= 128 registers
-constexpr uint32_t SMEM_TC2 = STAGE_BYTES_TC + 1024;
-
-__global__ void __launch_bounds__(kThreadsTc2, 2)
-attn_space_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                      const Desc d, int q_rows_outer, int q_rows_inner, int kv_rows_outer, int kv_rows_inner) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[5];       // full | s_ready p_ready o_ready tmem_free
-    __shared__ uint32_t tmem_slot;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t *base_g = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bar0 = smem_u32(bars);
-    const uint32_t full_bar = bar0, s_bar = bar0 + 8, p_bar = bar0 + 16, o_bar = bar0 + 24, free_bar = bar0 + 32;
-    const int Lkp = d.Lk + d.has_prefix;
-    const int n_tiles = (d.Lq + 127) / 128;
-    const int prob = blockIdx.x;
-    const int h = prob % d.n_heads;
-    const int i = (prob / d.n_heads) % d.n_inner;
-    const int o = prob / (d.n_heads * d.n_inner);
-    const uint32_t sQ = base, sK = sQ + Q_BYTES, sV = sK + KV_BYTES;
-
-    // rows the TMA boxes do not write must be finite: query rows Lq..255, key / value rows Lk(+1)..207
-    for (uint32_t c = threadIdx.x; c < (256u - d.Lq) * 8u; c += kThreadsTc2) reinterpret_cast<uint4 *>(base_g + d.Lq * 128)[c] = make_uint4(0, 0, 0, 0);
-    for (uint32_t c = threadIdx.x; c < (KV_ROWS - d.Lk) * 8u; c += kThreadsTc2) {
-        reinterpret_cast<uint4 *>(base_g + Q_BYTES + d.Lk * 128)[c] = make_uint4(0, 0, 0, 0);
-        reinterpret_cast<uint4 *>(base_g + Q_BYTES + KV_BYTES + d.Lk * 128)[c] = make_uint4(0, 0, 0, 0);
-    }
-    if (warp == 4 && lane == 0) {
-        mbar_init(full_bar, 2);
-        mbar_init(s_bar, 1);
-        mbar_init(p_bar, 4);
-        mbar_init(o_bar, 1);
-        mbar_init(free_bar, 4);
-        fence_barrier_init();
-    }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
-
-    if (warp == 5) {
-        // ================================ producer ====================================
-        if (lane == 0) {
-            mbar_arrive_expect_tx(full_bar, static_cast<uint32_t>(d.Lq + 2 * d.Lk) * 128u);
-            tma_load_2d(sQ, &tm_q, full_bar, h * HD, o * q_rows_outer + i * q_rows_inner);
-            tma_load_2d(sK, &tm_k, full_bar, h * HD, o * kv_rows_outer + i * kv_rows_inner);
-            tma_load_2d(sV, &tm_v, full_bar, h * HD, o * kv_rows_outer + i * kv_rows_inner);
-        }
-        if (d.has_prefix && lane < 16) {               // the CLS key / value row -> row d.Lk of the K / V tiles (overwrites the zero fill)
-            const int cc = lane & 7, r = d.Lk;
-            cp_async16((lane < 8 ? sK : sV) + r * 128 + ((cc ^ (r & 7)) << 4), (lane < 8 ? d.kp : d.vp) + o * d.prefix_outer + h * HD + cc * 8);
-        }
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar);
-    } else if (warp == 4) {
-        // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            const uint32_t idesc_s = make_idesc_major(128, KV_ROWS, 0, 0);
-            const uint32_t idesc_o = make_idesc_major(128, HD, 0, 1);
-            mbar_wait(full_bar, 0);
-            tc_fence_after();
-            for (int t = 0; t < n_tiles; ++t) {
-                if (t > 0) {
-                    mbar_wait(free_bar, (t - 1) & 1);           // O of the previous tile has been read out of TMEM
-                    tc_fence_after();
-                }
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_bf16(tmem_base, make_sw128_desc(sQ + t * 16384 + k * 32), make_sw128_desc(sK + k * 32), idesc_s, static_cast<uint32_t>(k != 0));
-                umma_commit(s_bar);
-                mbar_wait(p_bar, t & 1);
-                tc_fence_after();
-#pragma unroll 1
-                for (int k = 0; k < static_cast<int>(KV_ROWS) / 16; ++k)
-                    umma_bf16_ts(tmem_base + O_COL, tmem_base + P_COL + k * 8, make_sw128_mn_desc(sV + k * 2048, KV_BYTES), idesc_o,
-                                 static_cast<uint32_t>(k != 0));
-                umma_commit(o_bar);
-            }
-        }
-    } else if (warp < 4) {
-        // ================================ softmax + epilogue ===========================
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-        const float sl2 = d.scale * 1.4426950408889634f;
-        for (int t = 0; t < n_tiles; ++t) {
-            const int row = t * 128 + warp * 32 + lane;
-            const bool rows_live = t * 128 + warp * 32 < d.Lq;
-            mbar_wait(s_bar, t & 1);
-            tc_fence_after();
-            float inv = 0.f;
-            if (rows_live) {
-                // two resident CTAs hide each other's latency, so the passes are kept simple (and under 128 registers)
-                uint32_t ra[32];
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < 6; ++c) {
-                    tmem_ld32(trow + c * 32, ra);
-                    tmem_ld_wait_dep(ra);
-                    if ((c + 1) * 32 <= Lkp) softmax_max32(ra, mx);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (c * 32 + j < Lkp) mx = fmaxf(mx, __uint_as_float(ra[j]));
-                    }
-                }
-                tmem_ld16_into32(trow + 192, ra);
-                tmem_ld_wait_dep(ra);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) if (192 + j < Lkp) mx = fmaxf(mx, __uint_as_float(ra[j]));
-                const float mxs = mx * sl2;
-                float sum = 0.f;
-                uint32_t pk[16];
-#pragma unroll 1
-                for (int c = 0; c < 6; ++c) {
-                    tmem_ld32(trow + c * 32, ra);
-                    tmem_ld_wait_dep(ra);
-                    if ((c + 1) * 32 <= Lkp) softmax_exp32(ra, pk, sl2, mxs, sum);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const float p0 = c * 32 + j < Lkp ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
-                            const float p1 = c * 32 + j + 1 < Lkp ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
-                            sum += p0 + p1;
-                            pk[j >> 1] = pack_bf16x2(p0, p1);
-                        }
-                    }
-                    tmem_st16(trow + P_COL + c * 16, pk);
-                }
-                {
-                    tmem_ld16_into32(trow + 192, ra);
-                    tmem_ld_wait_dep(ra);
-                    uint32_t pt[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const float p0 = 192 + j < Lkp ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
-                        const float p1 = 192 + j + 1 < Lkp ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
-                        sum += p0 + p1;
-                        pt[j >> 1] = pack_bf16x2(p0, p1);
-                    }
-                    tmem_st8(trow + P_COL + 96, pt);
-                }
-                tmem_st_wait();
-                inv = 1.0f / sum;
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_bar);
-            mbar_wait(o_bar, t & 1);
-            tc_fence_after();
-            uint32_t o0[32], o1[32];
-            if (rows_live) {
-                tmem_ld32(trow + O_COL, o0);
-                tmem_ld32(trow + O_COL + 32, o1);
-                tmem_ld_wait();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(free_bar);
-            if (rows_live && row < d.Lq) {
-                uint4 *og = reinterpret_cast<uint4 *>(d.out + o * d.o_outer + i * d.o_inner + static_cast<int64_t>(row) * d.o_row + h * HD);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    og[k] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * k]) * inv, __uint_as_float(o0[8 * k + 1]) * inv),
-                                       pack_bf16x2(__uint_as_float(o0[8 * k + 2]) * inv, __uint_as_float(o0[8 * k + 3]) * inv),
-                                       pack_bf16x2(__uint_as_float(o0[8 * k + 4]) * inv, __uint_as_float(o0[8 * k + 5]) * inv),
-                                       pack_bf16x2(__uint_as_float(o0[8 * k + 6]) * inv, __uint_as_float(o0[8 * k + 7]) * inv));
-                    og[4 + k] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * k]) * inv, __uint_as_float(o1[8 * k + 1]) * inv),
-                                           pack_bf16x2(__uint_as_float(o1[8 * k + 2]) * inv, __uint_as_float(o1[8 * k + 3]) * inv),
-                                           pack_bf16x2(__uint_as_float(o1[8 * k + 4]) * inv, __uint_as_float(o1[8 * k + 5]) * inv),
-                                           pack_bf16x2(__uint_as_float(o1[8 * k + 6]) * inv, __uint_as_float(o1[8 * k + 7]) * inv));
-                }
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 4) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
-    }
-}
-
 }  // namespace
 
 bool tc_supported(const Desc &d) {
@@ -584,14 +390,6 @@ int launch_tc(const Desc &d, cudaStream_t st) {
         if (rc == SFB_OK) rc = encode_tmap_bf16_2d(&tv, d.v, kv_rows, d.n_heads * HD, d.kv_row, d.Lk, HD);
         if (rc != SFB_OK) return rc;
         use_tma = 1;
-    }
-    static const int variant = getenv("SFB_ATTN_TC_VARIANT") ? atoi(getenv("SFB_ATTN_TC_VARIANT")) : 1;   // 1 = persistent (default: measured 2.2 vs 3.0 ms), 2 = two CTAs per SM
-    if (use_tma && variant == 2 && d.xq == nullptr) {
-        static PerDeviceOnce attr_once2;
-        if (attr_once2.first()) SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC2));
-        attn_space_tc2_kernel<<<static_cast<unsigned>(n_prob), kThreadsTc2, SMEM_TC2, st>>>(tq, tk, tv, d, qo, qi, ko, ki);
-        SFB_CHECK_LAUNCH();
-        return SFB_OK;
     }
     const unsigned grid = static_cast<unsigned>(n_prob < num_sms() ? n_prob : num_sms());
     attn_space_tc_kernel<<<grid, kThreadsTc, SMEM_TC, st>>>(tq, tk, tv, d, static_cast<int>(n_prob), use_tma, qo, qi, ko, ki);

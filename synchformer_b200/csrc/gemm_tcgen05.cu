@@ -376,6 +376,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int k = 0; k < 8; ++k)
                             *reinterpret_cast<float4 *>(st_row + ((k ^ (lane & 7)) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                         __syncwarp();
+                        float e1[8], e2[8];          // EMIT_LN: this lane's 4-column partial (sum, sum of squares) of rows 4 i + rr
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rloc = 4 * i + rr;
@@ -386,18 +387,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                 if (has_res) val.x += res[i].x, val.y += res[i].y, val.z += res[i].z, val.w += res[i].w;
                                 if (do_store) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + grow * p.ldo + gcol) = val;
                             }
-                            if (emit_ln) {          // warp-uniform
+                            if (emit_ln) {          // compile-time
                                 if (inb && do_store)
                                     *reinterpret_cast<uint2 *>(p.emit_bf16 + grow * p.ld_emit + gcol) = make_uint2(pack_bf16x2(val.x, val.y), pack_bf16x2(val.z, val.w));
-                                float s1 = inb ? (val.x + val.y) + (val.z + val.w) : 0.f;
-                                float s2 = inb ? fmaf(val.x, val.x, fmaf(val.y, val.y, fmaf(val.z, val.z, val.w * val.w))) : 0.f;
-#pragma unroll
-                                for (int o = 1; o < 8; o <<= 1) {        // the 8 lanes that share rr hold the 32 columns of one row
-                                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                                }
-                                if (cc == i) ln_ps += s1, ln_pq += s2;
+                                e1[i] = inb ? (val.x + val.y) + (val.z + val.w) : 0.f;
+                                e2[i] = inb ? fmaf(val.x, val.x, fmaf(val.y, val.y, fmaf(val.z, val.z, val.w * val.w))) : 0.f;
                             }
+                        }
+                        if (emit_ln) {
+                            // The 8 lanes that share rr hold 4 columns each of rows 4 i + rr, i = 0..7.  Transposing reduction: every exchange
+                            // halves the number of rows a lane is responsible for (7 shuffles per statistic instead of 24 butterflies), and lane
+                            // cc ends up with the total of row 4 cc + rr.
+                            const bool h4 = (cc & 4) != 0, h2 = (cc & 2) != 0, h1 = (cc & 1) != 0;
+                            float b1[4], b2[4], c1[2], c2[2];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                b1[j] = (h4 ? e1[j + 4] : e1[j]) + __shfl_xor_sync(0xffffffffu, h4 ? e1[j] : e1[j + 4], 4);
+                                b2[j] = (h4 ? e2[j + 4] : e2[j]) + __shfl_xor_sync(0xffffffffu, h4 ? e2[j] : e2[j + 4], 4);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                c1[j] = (h2 ? b1[j + 2] : b1[j]) + __shfl_xor_sync(0xffffffffu, h2 ? b1[j] : b1[j + 2], 2);
+                                c2[j] = (h2 ? b2[j + 2] : b2[j]) + __shfl_xor_sync(0xffffffffu, h2 ? b2[j] : b2[j + 2], 2);
+                            }
+                            ln_ps += (h1 ? c1[1] : c1[0]) + __shfl_xor_sync(0xffffffffu, h1 ? c1[0] : c1[1], 1);
+                            ln_pq += (h1 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? c2[0] : c2[1], 1);
                         }
                         __syncwarp();
                     }

@@ -224,6 +224,36 @@ def test_divided_attention_views(cuda_device, impl, mode):
     assert (got - ref).abs().max() < 3e-2
 
 
+@pytest.mark.parametrize('q_gain,k_gain', [(9.0, 9.0), (0.01, 0.01), (30.0, 0.02), (1.0, 1.0)])
+def test_space_attention_softmax_reference_value(cuda_device, q_gain, k_gain):
+    """Softmax range handling of the tcgen05 space-attention kernel against fp32 torch: huge logits (gains 9 x 9: near one-hot rows, scores
+    of several hundred), tiny and mixed magnitudes, and rows whose queries differ by orders of magnitude inside one warp - nothing may
+    overflow, underflow to a zero row sum, or lose the bf16 precision of the probabilities."""
+    from synchformer_b200 import ops
+    n, D = 1, 768
+    g = torch.Generator(device='cuda').manual_seed(int(q_gain * 100 + k_gain * 7))
+    raw = torch.randn(n * 1569, 3 * D, device='cuda', generator=g)
+    raw[:, :D] *= q_gain
+    raw[:, D:2 * D] *= k_gain
+    raw[5::7, :D] *= 40.0                                                          # a few rows with much larger queries
+    qkv = _bf(raw)
+    att = torch.zeros(n * 1569, D, device='cuda', dtype=torch.bfloat16)
+    row, seg = 3 * D, 1569 * 3 * D
+    t = qkv.float().view(n, 1569, 3, 12, 64)
+    q, k, v = t[:, :, 0].permute(0, 2, 1, 3), t[:, :, 1].permute(0, 2, 1, 3), t[:, :, 2].permute(0, 2, 1, 3)
+    q_, k_, v_ = [x[:, :, 1:].reshape(n, 12, 8, 196, 64) for x in (q, k, v)]
+    kk = torch.cat([k[:, :, :1].unsqueeze(2).expand(n, 12, 8, 1, 64), k_], 3)
+    vv = torch.cat([v[:, :, :1].unsqueeze(2).expand(n, 12, 8, 1, 64), v_], 3)
+    ref = _ref_attention(q_, kk, vv, 0.125).reshape(n, 12, 1568, 64)
+    ops.attention(qkv[1:], qkv[1:, D:], qkv[1:, 2 * D:], att[1:], q_strides=(seg, 196 * row, row), kv_strides=(seg, 196 * row, row),
+                  o_strides=(1569 * D, 196 * D, D), n_outer=n, n_inner=8, n_heads=12, head_dim=64, Lq=196, Lk=196, scale=0.125,
+                  k_prefix=qkv[:, D:], v_prefix=qkv[:, 2 * D:], prefix_outer=seg)
+    torch.cuda.synchronize()
+    got = att.view(n, 1569, 12, 64)[:, 1:].permute(0, 2, 1, 3).float()
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, ref) < 8e-3, (q_gain, k_gain, rel_l2(got, ref))
+
+
 @pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(1, id='simple')])
 @pytest.mark.parametrize('L,heads,hd', [(74, 12, 64), (198, 8, 96), (114, 8, 96), (30, 8, 96), (16, 12, 64), (17, 12, 64)])
 def test_plain_self_attention(cuda_device, impl, L, heads, hd):

@@ -1,4 +1,4 @@
-"""BASELINE.json config 5 at N > 1: clips/s for a GLOBAL batch in {1, 8, 32, 128, 256} x segments in {8, 14}, the flattened (clip, segment)
+"""BASELINE.json config 5 at N > 1: clips/s for a GLOBAL batch in {1, 8, 32, 64, 128, 256} x segments in {8, 14}, the flattened (clip, segment)
 list sharded over the ranks (parallel.synchformer_forward_sharded: one all-gather of segment features, sync transformer on a clip range,
 one tiny all-gather of logits) - strong scaling at fixed global work.  Launch:
 
@@ -25,7 +25,7 @@ def main():
     out = []
     for S in (8, 14):
         model = M.build_synchformer(n_segments=S, state_dict=synth.synthetic_state_dict(1337, n_segments=S), device=dev)
-        for B in (1, 8, 32, 128, 256):
+        for B in (1, 8, 32, 64, 128, 256):
             s0, s1 = parallel.shard_range(B * S, world, rank)
             n = s1 - s0
             g = torch.Generator(device=dev).manual_seed(rank)
