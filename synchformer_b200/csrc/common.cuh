@@ -47,11 +47,10 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 
 // Exact-erf GELU for kernel epilogues, two elements per call on the packed fp32x2 pipe of sm_100 (FFMA2 / FMUL2).
 //   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2)
-//   erfc(z) = 1 / (1 + a1 z + a2 z^2 + ... + a6 z^6)^16                                          (Abramowitz-Stegun 7.1.28,
-//   |erf error| <= 3e-7; measured max |gelu error| 7.1e-7 over [-12, 12], i.e. fp32 round-off level and far below the bf16 rounding of
-//   the value that is stored).  Branch-free; per PAIR of elements: 2 MUFU (rcp) + 13 packed FMA-pipe instructions.  Round 1 used 7.1.26
-//   (rcp + ex2 per element): the fc1 epilogue sat at 40 % XU utilisation, and MUFU issue is 4 lanes / clock against 32 for the FMA pipe.
-//   For |x| > ~19 the 16th power overflows to +inf and rcp returns 0: gelu(x) = max(x, 0) exactly, no NaN.
+//   erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),  t = 1 / (1 + p z)        (Abramowitz-Stegun 7.1.26,
+//   |erf error| <= 1.5e-7, i.e. fp32 round-off level; measured max |gelu error| 3.3e-7 over [-12, 12]).
+// With zs = |x| sqrt(log2(e) / 2): exp(-z^2) = 2^(-zs^2), p and the 0.5 are folded into the constants.  Branch-free;
+// per PAIR of elements: 4 MUFU (2 rcp, 2 ex2) + ~11 packed FMA-pipe instructions, against ~60 for two erff() calls.
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
     uint64_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -81,21 +80,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ void gelu_erf_fast2(float &x0, float &x1) {
     const float a0 = fabsf(x0), a1 = fabsf(x1);
     const uint64_t ax = pack_f32x2(a0, a1);
-    const uint64_t z = mul_f32x2(ax, pack_f32x2(0.70710678f, 0.70710678f));
-    uint64_t p = fma_f32x2(z, pack_f32x2(0.0000430638f, 0.0000430638f), pack_f32x2(0.0002765672f, 0.0002765672f));
-    p = fma_f32x2(z, p, pack_f32x2(0.0001520143f, 0.0001520143f));
-    p = fma_f32x2(z, p, pack_f32x2(0.0092705272f, 0.0092705272f));
-    p = fma_f32x2(z, p, pack_f32x2(0.0422820123f, 0.0422820123f));
-    p = fma_f32x2(z, p, pack_f32x2(0.0705230784f, 0.0705230784f));
-    p = fma_f32x2(z, p, pack_f32x2(1.0f, 1.0f));
-    p = mul_f32x2(p, p);
-    p = mul_f32x2(p, p);
-    p = mul_f32x2(p, p);
-    p = mul_f32x2(p, p);
+    const uint64_t zs = mul_f32x2(ax, pack_f32x2(0.84932178f, 0.84932178f));
+    const uint64_t den = fma_f32x2(zs, pack_f32x2(0.27273747f, 0.27273747f), pack_f32x2(1.0f, 1.0f));
     float d0, d1;
-    unpack_f32x2(p, d0, d1);
+    unpack_f32x2(den, d0, d1);
+    const uint64_t t = pack_f32x2(rcp_approx(d0), rcp_approx(d1));
+    uint64_t poly = fma_f32x2(t, pack_f32x2(0.53070271f, 0.53070271f), pack_f32x2(-0.72657603f, -0.72657603f));
+    poly = fma_f32x2(t, poly, pack_f32x2(0.71070689f, 0.71070689f));
+    poly = fma_f32x2(t, poly, pack_f32x2(-0.14224836f, -0.14224836f));
+    poly = fma_f32x2(t, poly, pack_f32x2(0.12741479f, 0.12741479f));
+    poly = mul_f32x2(poly, t);
+    float s0, s1;
+    unpack_f32x2(mul_f32x2(zs, zs), s0, s1);
+    const uint64_t e = pack_f32x2(ex2_approx(-s0), ex2_approx(-s1));
     float h0, h1;
-    unpack_f32x2(mul_f32x2(mul_f32x2(ax, pack_f32x2(0.5f, 0.5f)), pack_f32x2(rcp_approx(d0), rcp_approx(d1))), h0, h1);
+    unpack_f32x2(mul_f32x2(mul_f32x2(ax, poly), e), h0, h1);
     x0 = fmaxf(x0, 0.0f) - h0;
     x1 = fmaxf(x1, 0.0f) - h1;
 }

@@ -25,6 +25,9 @@
 //   SFB_GEMM_LN_FOLD  the consumer (qkv / fc1) multiplies the UN-normalised xb by weights with gamma folded in and applies
 //                         out = rstd_row (acc - mean_row colsum_j) + bias'_j        colsum_j = sum_k bf16(gamma_k W_jk),  bias' = b + W beta
 //                     in its epilogue - algebraically LayerNorm(x) W^T + b with the same bf16 operand rounding budget as the unfused path
+// Epilogue experiments measured on the B200 in round 2 and NOT adopted (tools/microbench.py, 512 segments): staging bias / column sums in
+// shared memory (needs a 4-stage ring: proj+res 1.27 -> 1.21 ms but fc2 2.90 -> 3.14 ms and the LN_FOLD variants slower), and a single-MUFU
+// GELU (Abramowitz-Stegun 7.1.28 instead of 7.1.26: fc1 3.29 vs 3.29 ms - the fc1 epilogue is not XU-bound).
 // Tiles are walked n-fastest so the CTAs that share an A row-block run at the same time and hit it in L2;
 // W (<= 4.7 MB) is L2-resident throughout.  M / N / K tails are handled by TMA zero fill + epilogue masking.
 //
@@ -51,19 +54,15 @@ constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;               // 16 KB: this CTA's 128 rows of A
 constexpr uint32_t EPI_WARP_BYTES = 4096;                        // 32 rows x 128 B transpose buffer per epilogue warp
 constexpr uint32_t TMEM_COLS = 512;
-// per-column epilogue vectors (bias, LN_FOLD column sums) staged in shared memory once per CTA: every epilogue thread needs every column
-// of its 64-column group, and with 227 KB of shared memory configured there is no L1 left to catch 16 broadcast LDGs per 32 columns
-constexpr int kVecMaxN = 3072;
-constexpr uint32_t VEC_BYTES = 2 * kVecMaxN * sizeof(float);     // 24 KB
 constexpr int kMaxStages = 6;
 
 template <int CG>
 struct Cfg {
-    static constexpr int kStages = CG == 2 ? 4 : 2;                // (cuBLAS' kernels for these shapes run 3-4 stages of the same tile)
+    static constexpr int kStages = CG == 2 ? 5 : 3;
     static constexpr int B_ROWS = BLOCK_N / CG;                   // W rows staged by one CTA
     static constexpr uint32_t B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB (pair) / 48 KB (single)
-    static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + VEC_BYTES + 1024;  // + 1024-byte alignment slack
+    static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024;  // + 1024-byte alignment slack
 };
 
 // experiment switches (env SFB_GEMM_DBG, measurement aid only: results are wrong when set): 1 = no global stores in the epilogue,
@@ -187,17 +186,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
-    float *vec_bias = reinterpret_cast<float *>(smem_raw + (tiles_base - smem_u32(smem_raw)) + kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES);
-    float *vec_cs = vec_bias + kVecMaxN;
-    const bool vec_staged = p.N <= kVecMaxN;
-    if (vec_staged) {
-        for (int i = threadIdx.x; i < p.N; i += kThreads) {
-            vec_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
-            if (EPI == EPI_BF16_LN) vec_cs[i] = __ldg(p.ln_colsum + i);
-        }
-    }
     tc_fence_before();
-    if (CG == 2) cluster_sync_all(); else __syncthreads();       // barriers initialised + TMEM allocated in every CTA of the cluster, vectors staged
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // barriers initialised + TMEM allocated in every CTA of the cluster
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
@@ -376,7 +366,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 if (col0 + j < p.N) {
-                                    const float4 b = vec_staged ? *reinterpret_cast<const float4 *>(vec_bias + col0 + j) : __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
                                     v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
                                 }
                             }
@@ -454,8 +444,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 if (cb + j < p.N) {
-                                    const float4 b = vec_staged ? *reinterpret_cast<const float4 *>(vec_bias + cb + j) : __ldg(reinterpret_cast<const float4 *>(p.bias + cb + j));
-                                    const float4 cs = vec_staged ? *reinterpret_cast<const float4 *>(vec_cs + cb + j) : __ldg(reinterpret_cast<const float4 *>(p.ln_colsum + cb + j));
+                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + j));
+                                    const float4 cs = __ldg(reinterpret_cast<const float4 *>(p.ln_colsum + cb + j));
                                     v[j] = fmaf(fmaf(nm, cs.x, v[j]), ln_rstd, b.x), v[j + 1] = fmaf(fmaf(nm, cs.y, v[j + 1]), ln_rstd, b.y);
                                     v[j + 2] = fmaf(fmaf(nm, cs.z, v[j + 2]), ln_rstd, b.z), v[j + 3] = fmaf(fmaf(nm, cs.w, v[j + 3]), ln_rstd, b.w);
                                 }
@@ -464,7 +454,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 if (cb + j < p.N) {
-                                    const float4 b = vec_staged ? *reinterpret_cast<const float4 *>(vec_bias + cb + j) : __ldg(reinterpret_cast<const float4 *>(p.bias + cb + j));
+                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + j));
                                     v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
                                 }
                             }
