@@ -15,7 +15,7 @@ cat $O/sweep_multi_n$N.jsonl | tee -a $O/summary_multi_n$N.txt
 if [ "$N" = "8" ]; then
   timeout 400 $TR tools/train_bench.py --batch 32 --segments 14 --steps 5 --warmup 3 2>$O/train_n8.err | tail -1 > $O/train_bench_sync_n8.json; echo "config 4 (DDP, 8 x 32 clips) rc=${PIPESTATUS[0]}" | tee -a $O/summary_multi_n$N.txt
   cat $O/train_bench_sync_n8.json | tee -a $O/summary_multi_n$N.txt
-  NCCL_DEBUG=INFO timeout 300 $TR bench.py --gpus 8 --steps 5 --warmup 3 2>$O/bench_n8.err | tail -1 > $O/bench_n8.json; echo "bench N=8 rc=${PIPESTATUS[0]}" | tee -a $O/summary_multi_n$N.txt
+  timeout 300 $TR bench.py --gpus 8 --steps 5 --warmup 3 2>$O/bench_n8.err | grep "^{\"metric\"" > $O/bench_n8.json; echo "bench N=8 rc=${PIPESTATUS[0]}" | tee -a $O/summary_multi_n$N.txt
   cat $O/bench_n8.json | cut -c1-600 | tee -a $O/summary_multi_n$N.txt
   grep -m3 -i "NVLS\|Using network\|via P2P" $O/bench_n8.err | tee -a $O/summary_multi_n$N.txt
 fi
