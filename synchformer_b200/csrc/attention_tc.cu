@@ -203,19 +203,24 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 for (int t = 0; t < n_tiles; ++t) {
                     mbar_wait(free_bar(t), (it & 1) ^ 1u);          // O_t of the previous problem has been read out
                     tc_fence_after();
+                    {   // descriptors differ by constants only: a fully unrolled sequence issues in ~56 clocks per tcgen05.mma, a rolled loop that
+                        // rebuilds them in ~150 (tools/ubench/mma_cost.cu)
+                        const uint64_t dq = make_sw128_desc(sQ + t * 16384), dk = make_sw128_desc(sK);
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        umma_bf16(tmem_base + t * TILE_COLS, make_sw128_desc(sQ + t * 16384 + k * 32), make_sw128_desc(sK + k * 32), idesc_s,
-                                  static_cast<uint32_t>(k != 0));
+                        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + t * TILE_COLS, dq + 2 * k, dk + 2 * k, idesc_s, static_cast<uint32_t>(k != 0));
+                    }
                     umma_commit(s_bar(t));
                 }
                 for (int t = 0; t < n_tiles; ++t) {
                     mbar_wait(p_bar(t), it & 1);                    // softmax has written P_t into TMEM
                     tc_fence_after();
-#pragma unroll 1
-                    for (int k = 0; k < static_cast<int>(KV_ROWS) / 16; ++k)
-                        umma_bf16_ts(tmem_base + t * TILE_COLS + O_COL, tmem_base + t * TILE_COLS + P_COL + k * 8,
-                                     make_sw128_mn_desc(sV + k * 2048, KV_BYTES), idesc_o, static_cast<uint32_t>(k != 0));
+                    {
+                        const uint64_t dv = make_sw128_mn_desc(sV, KV_BYTES);
+                        const uint32_t to = tmem_base + t * TILE_COLS + O_COL, tp = tmem_base + t * TILE_COLS + P_COL;
+#pragma unroll
+                        for (int k = 0; k < static_cast<int>(KV_ROWS) / 16; ++k)          // 16 keys = 2 KB of V = 128 units of the descriptor's address field
+                            umma_bf16_ts(to, tp + k * 8, dv + 128 * k, idesc_o, static_cast<uint32_t>(k != 0));
+                    }
                     umma_commit(o_bar(t));
                 }
                 umma_commit(empty_bar(s));                          // every MMA that reads this stage has been issued

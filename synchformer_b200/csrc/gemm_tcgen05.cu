@@ -87,6 +87,7 @@ struct EpiParams {
     float *emit_stats;        // EMIT_LN: [M][N / 64][2]
     __nv_bfloat16 *emit_bf16; // EMIT_LN: bf16 copy of the output rows, row stride ld_emit
     int64_t ld_emit;
+    int tma_store;            // bf16 output tiles leave through cp.async.bulk.tensor (UTMASTG) instead of per-thread st.global
 };
 
 // ------------------------------------------------------------------------------------------ cluster helpers
@@ -129,6 +130,15 @@ __device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t cta_mask)
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
                  : "memory");
 }
+// TMA store of one shared-memory box (generic-proxy writes must be fenced with fence.proxy.async first); bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the bit that distinguishes the two CTAs of a pair in a shared-window address
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -142,7 +152,8 @@ enum { EPI_BF16 = 0, EPI_BF16_LN = 1, EPI_F32 = 2, EPI_F32_LN = 3 };
 
 template <int CG, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)   // 18 warps are allocated as 20 (granularity 4): 96 registers per thread
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const EpiParams p) {
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                         const __grid_constant__ CUtensorMap tmap_out, const EpiParams p) {
     using C = Cfg<CG>;
     constexpr int CL = CG;
     constexpr int kStages = C::kStages;
@@ -165,6 +176,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
+        if (p.tma_store) tma_prefetch_desc(&tmap_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -233,6 +245,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // ================================ MMA issuer (pair leader only) ================
         if (lane == 0 && rank == 0) {
             constexpr uint32_t idesc = make_idesc(BLOCK_M * CG, BLOCK_N);
+            const uint64_t desc0 = make_sw128_desc(tiles_base);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -242,13 +255,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t sa = tiles_base + stage * STAGE_BYTES;
-                    const uint32_t sb = sa + A_BYTES;
+                    // descriptors of a stage differ from `desc0` by constants (address field = bytes >> 4): the issue sequence is four
+                    // tcgen05.mma with immediate-offset operands - a sequence that rebuilds descriptors from addresses issues ~3x slower
+                    // (tools/ubench/mma_cost.cu: ~150 vs ~56 clocks per instruction, against 128 clocks of tensor-pipe work each)
+                    const uint64_t da = desc0 + static_cast<uint64_t>(stage * (STAGE_BYTES >> 4)), db = da + (A_BYTES >> 4);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t da = make_sw128_desc(sa + k * UMMA_K * 2), db = make_sw128_desc(sb + k * UMMA_K * 2);
-                        if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, static_cast<uint32_t>((kb | k) != 0));
-                        else umma_bf16(tmem_d, da, db, idesc, static_cast<uint32_t>((kb | k) != 0));
+                        const uint32_t acc_flag = k != 0 ? 1u : static_cast<uint32_t>(kb != 0);
+                        if (CG == 2) umma_bf16_cg2(tmem_d, da + 2 * k, db + 2 * k, idesc, acc_flag);
+                        else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, acc_flag);
                     }
                     if (CG == 2) umma_commit_cg2(empty_bar(stage), static_cast<uint16_t>(3u)); else umma_commit(empty_bar(stage));   // smem stage reusable
                     if (++stage == kStages) {
@@ -427,6 +442,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             } else {
                 const int col0 = n0;
+                if (p.tma_store) {        // the previous tile's TMA store must have finished READING this warp's staging buffer
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
                 {
 #pragma unroll
                     for (int hseg = 0; hseg < 2; ++hseg) {
@@ -470,7 +489,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                            pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
                     }
                 }
-                if (col0 < p.N) {
+                if (col0 < p.N && p.tma_store) {
+                    // the staging buffer IS the box layout of the output tensor map (32 rows x 128 B, 16-byte chunks XOR-swizzled by row):
+                    // one elected lane hands it to the TMA unit, which clips rows >= M / columns >= N itself
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && do_store) {
+                        tma_store_2d(&tmap_out, smem_u32(stage), col0, m0);
+                        tma_store_commit();
+                    }
+                } else if (col0 < p.N) {
                     __syncwarp();
                     const int gcol = col0 + cc * 8;
 #pragma unroll
@@ -489,6 +517,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 acc_phase ^= 1u;
             }
         }
+        if (!out_f32 && p.tma_store && lane == 0) tma_store_wait_all();      // smem must outlive the bulk stores that read it
     }
 
     tc_fence_before();
@@ -631,6 +660,15 @@ extern "C" int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const
     if (rc != SFB_OK) return rc;
     rc = make_tmap(&tmap_w, W, N, K, K, BLOCK_N / cg);           // rows of W fetched by one CTA per k-block
     if (rc != SFB_OK) return rc;
+    // bf16 outputs leave through TMA stores: one 32-row x 64-column box per epilogue warp (SFB_GEMM_TMA_STORE=0: per-thread st.global, A/B aid)
+    static const int tma_store_env = getenv("SFB_GEMM_TMA_STORE") ? atoi(getenv("SFB_GEMM_TMA_STORE")) : 1;
+    CUtensorMap tmap_out = tmap_a;
+    p.tma_store = 0;
+    if (tma_store_env && !(flags & SFB_GEMM_OUT_F32)) {
+        rc = encode_tmap_bf16_2d(&tmap_out, out, M, N, ldo, 32, 64);
+        if (rc != SFB_OK) return rc;
+        p.tma_store = 1;
+    }
 
     static PerDeviceOnce attr_once;
     if (attr_once.first()) {
@@ -653,7 +691,7 @@ extern "C" int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const
     const int max_clusters = num_sms() / cg;
     const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
     cfg.gridDim = dim3(cg * clusters);
-#define SFB_GEMM_LAUNCH(CGV, EPIV) SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<CGV, EPIV>, tmap_a, tmap_w, p))
+#define SFB_GEMM_LAUNCH(CGV, EPIV) SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<CGV, EPIV>, tmap_a, tmap_w, tmap_out, p))
     if (cg == 2) {
         switch (epi) {
             case EPI_BF16: SFB_GEMM_LAUNCH(2, EPI_BF16); break;
