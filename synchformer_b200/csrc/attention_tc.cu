@@ -18,13 +18,19 @@
 // range as the softmax consumes S; O accumulates in columns [128,192) once S is dead.
 // Nothing touches HBM between the qkv activations and the attention output.
 //
-// What bounds it (round 2, clock64 phase stamps of one CTA, tools/attn_modes.py): a problem takes ~9 600 clocks = S MMAs 1 450 (4
-// instructions, ~420 clocks of tensor work: the rest is issue -> commit -> waiter latency) -> row-max pass 850 -> exp2 pass 3 400 (the two
-// tiles' warps share the XU pipe) -> P V 1 600 (13 small M128 N64 K16 instructions at ~120 clocks each) -> O read / barrier hops.  Tried and
-// measured, not adopted: a single-pass softmax whose reference value is the Cauchy-Schwarz bound |q| max|k| scale (the max pass is only 8 %
-// of the time; computing the norms from shared memory plus a named barrier cost 30 %), and a software-pipelined issue order
-// S(0,i) PV(1,i-1) S(1,i) PV(0,i) (the in-order tensor pipe re-locks the two tiles; no gain).  The next step is more independent items
-// in flight per SM (cta_group::2 pairs: one 128-row tile per CTA, two problems in the 512 TMEM columns).
+// What bounds it (round 2, clock64 phase stamps of one CTA, tools/attn_pipe.py; 1.76 -> 1.19 ms per launch at 512 segments):
+//   * the MMA phases are short bursts whose cost is issue + ~400 clocks of commit latency, not tensor work: fully unrolled issue sequences
+//     with constant-offset descriptors (56 instead of 150 clocks per tcgen05.mma, tools/ubench/mma_cost.cu);
+//   * the two tiles of a problem must not run in lock-step: issue order S(0,i) PV(1,i-1) S(1,i) PV(0,i) puts one tile's exp2 pass (XU
+//     pipe) next to the other tile's MMA / barrier latencies (tools/ubench/mma_commit_order.cu: a commit's barrier is not delayed by MMAs
+//     issued after it);
+//   * a row-per-thread st.global of the output (32 different lines per instruction) held the softmax warps ~1 800 clocks per problem:
+//     rows go to a swizzled staging tile and leave through one TMA store per tile, issued by the otherwise idle producer warp;
+//   * three integer divisions by run-time divisors at the top of every iteration (~430 clocks) moved behind the wait for P V;
+//   * the loop body of the softmax warps has to fit the instruction cache: the masked variants of the chunk code are compiled out for
+//     Lk >= 192 and the chunk loops are rolled (89 KB -> 58 KB of SASS: 1.37 -> 1.19 ms on its own).
+// Tried and measured, not adopted: a single-pass softmax whose reference value is the Cauchy-Schwarz bound |q| max|k| scale (the max
+// pass is only 8 % of the time; the norms from shared memory plus a named barrier cost 30 %).
 #include <stdlib.h>
 #include <string.h>
 
@@ -39,6 +45,9 @@ using namespace sfb::tc;
 
 namespace {
 
+// phase timestamps of CTA 0 (experiment aid, dbg == nullptr on the product path): dbg[it * 24 + slot] = clock64()
+#define SFB_TS(slot) do { if (dbg != nullptr && blockIdx.x == 0 && it < 12 && lane == 0) dbg[it * 24 + (slot)] = clock64(); } while (0)
+
 constexpr int HD = 64;
 constexpr int kSoftmaxWarps = 8, kProducerWarps = 3;   // 12 warps: 170 registers per thread are available
 constexpr int kThreadsTc = (kSoftmaxWarps + 1 + kProducerWarps) * 32;   // 384
@@ -46,7 +55,8 @@ constexpr uint32_t Q_BYTES = 256 * 128;                                 // two 1
 constexpr uint32_t KV_ROWS = 208;                                       // keys padded to a multiple of 16
 constexpr uint32_t KV_BYTES = KV_ROWS * 128;                            // 26 KB, a multiple of 1024
 constexpr uint32_t STAGE_BYTES_TC = Q_BYTES + 2 * KV_BYTES;             // 84 KB
-constexpr uint32_t SMEM_TC = 2 * STAGE_BYTES_TC + 1024;
+constexpr uint32_t O_STAGE_BYTES = 128 * 128;                           // one tile's bf16 output rows (128 rows x 64 dims), 128B-swizzled
+constexpr uint32_t SMEM_TC = 2 * STAGE_BYTES_TC + 2 * O_STAGE_BYTES + 1024;
 constexpr uint32_t TILE_COLS = 256, P_COL = 0, O_COL = 128;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
@@ -75,12 +85,17 @@ __device__ __forceinline__ void softmax_exp32(const uint32_t (&r)[32], uint32_t 
     sum += s0 + s1;
 }
 
+// kFull192: Lk >= 192, i.e. the six 32-column chunks of a score row are never masked (the product shape, Lk = 196): the masked variants of
+// the chunk code are not generated, which halves the softmax warps' loop body (89 KB of SASS for the generic kernel)
+template <bool kFull192>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                     const Desc d, int n_prob, int use_tma, int q_rows_outer, int q_rows_inner, int kv_rows_outer, int kv_rows_inner) {
+                     const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1, int tma_out, int o_rows_outer, int o_rows_inner,
+                     const Desc d, int n_prob, int use_tma, int q_rows_outer, int q_rows_inner, int kv_rows_outer, int kv_rows_inner, int pipe,
+                     long long *dbg) {
     extern __shared__ uint8_t smem_raw[];
     // barriers: full[2] empty[2] | s_ready[2] p_ready[2] o_ready[2] tmem_free[2]
-    __shared__ __align__(8) uint64_t bars[12];
+    __shared__ __align__(8) uint64_t bars[16];      // ... | o_stage_full[2] o_stage_free[2] (output staging tiles <-> store-issuing warp)
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -92,6 +107,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     auto p_bar = [&](int t) { return bar0 + 8u * (6 + t); };
     auto o_bar = [&](int t) { return bar0 + 8u * (8 + t); };
     auto free_bar = [&](int t) { return bar0 + 8u * (10 + t); };
+    auto ofull_bar = [&](int t) { return bar0 + 8u * (12 + t); };
+    auto ofree_bar = [&](int t) { return bar0 + 8u * (14 + t); };
     const int Lkp = d.Lk + d.has_prefix;            // <= 208; key row d.Lk is the prefix (CLS) row
     const int n_tiles = (d.Lq + 127) / 128;         // 2 for the space attention
 
@@ -107,6 +124,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             mbar_init(p_bar(t), 4);
             mbar_init(o_bar(t), 1);
             mbar_init(free_bar(t), 4);
+            mbar_init(ofull_bar(t), 4);
+            mbar_init(ofree_bar(t), 1);
         }
         fence_barrier_init();
     }
@@ -129,7 +148,24 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         // ================================ producers ===================================
         const int pw = warp - 9;                        // 0..2
         if (use_tma && pw >= 2) {
-            // idle
+            // warp 11: issues the output TMA stores, so that neither the issue (~500 clocks) nor the wait for the bulk read of the staging
+            // tile sits on a softmax warp.  Tiles complete in the order 0, 1 within a problem.
+            if (tma_out && lane == 0) {
+                int it = 0;
+                for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
+                    const int h = prob % d.n_heads, i = (prob / d.n_heads) % d.n_inner, o = prob / (d.n_heads * d.n_inner);
+                    for (int t = 0; t < n_tiles; ++t) {
+                        mbar_wait(ofull_bar(t), it & 1);                 // the tile's 4 warps have written (and fenced) their rows
+                        tma_store_2d(t == 0 ? &tm_o0 : &tm_o1, base + 2 * STAGE_BYTES_TC + t * O_STAGE_BYTES, h * HD, o * o_rows_outer + i * o_rows_inner + t * 128);
+                        tma_store_commit();
+                    }
+                    // both stores of this problem have finished READING shared memory -> the tiles may be rewritten (a full period later)
+                    tma_store_wait_read();
+                    mbar_arrive(ofree_bar(0));
+                    mbar_arrive(ofree_bar(1));
+                }
+                tma_store_wait_all();                                    // shared memory must outlive the bulk stores reading it
+            }
         } else {
             int it = 0;
             for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
@@ -194,36 +230,72 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         if (lane == 0) {
             const uint32_t idesc_s = make_idesc_major(128, KV_ROWS, 0, 0);     // S = Q K^T, both K-major
             const uint32_t idesc_o = make_idesc_major(128, HD, 0, 1);          // O = P V, V is MN-major
-            int it = 0;
-            for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
-                const int s = it & 1;
-                const uint32_t sQ = base + s * STAGE_BYTES_TC, sK = sQ + Q_BYTES, sV = sK + KV_BYTES;
-                mbar_wait(full_bar(s), (it >> 1) & 1);
+            // descriptors differ by constants only: a fully unrolled sequence issues in ~56 clocks per tcgen05.mma, a rolled loop that
+            // rebuilds them in ~150 (tools/ubench/mma_cost.cu)
+            auto issue_s = [&](int t, int it_) {
+                const uint32_t sQ = base + (it_ & 1) * STAGE_BYTES_TC, sK = sQ + Q_BYTES;
+                mbar_wait(free_bar(t), (it_ & 1) ^ 1u);             // O_t of the previous problem has been read out
                 tc_fence_after();
-                for (int t = 0; t < n_tiles; ++t) {
-                    mbar_wait(free_bar(t), (it & 1) ^ 1u);          // O_t of the previous problem has been read out
-                    tc_fence_after();
-                    {   // descriptors differ by constants only: a fully unrolled sequence issues in ~56 clocks per tcgen05.mma, a rolled loop that
-                        // rebuilds them in ~150 (tools/ubench/mma_cost.cu)
-                        const uint64_t dq = make_sw128_desc(sQ + t * 16384), dk = make_sw128_desc(sK);
+                const uint64_t dq = make_sw128_desc(sQ + t * 16384), dk = make_sw128_desc(sK);
 #pragma unroll
-                        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + t * TILE_COLS, dq + 2 * k, dk + 2 * k, idesc_s, static_cast<uint32_t>(k != 0));
-                    }
-                    umma_commit(s_bar(t));
-                }
-                for (int t = 0; t < n_tiles; ++t) {
-                    mbar_wait(p_bar(t), it & 1);                    // softmax has written P_t into TMEM
-                    tc_fence_after();
-                    {
-                        const uint64_t dv = make_sw128_mn_desc(sV, KV_BYTES);
-                        const uint32_t to = tmem_base + t * TILE_COLS + O_COL, tp = tmem_base + t * TILE_COLS + P_COL;
+                for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + t * TILE_COLS, dq + 2 * k, dk + 2 * k, idesc_s, static_cast<uint32_t>(k != 0));
+                umma_commit(s_bar(t));
+            };
+            auto issue_pv = [&](int t, int it_) {
+                const uint32_t sV = base + (it_ & 1) * STAGE_BYTES_TC + Q_BYTES + KV_BYTES;
+                mbar_wait(p_bar(t), it_ & 1);                       // softmax has written P_t into TMEM
+                tc_fence_after();
+                const uint64_t dv = make_sw128_mn_desc(sV, KV_BYTES);
+                const uint32_t to = tmem_base + t * TILE_COLS + O_COL, tp = tmem_base + t * TILE_COLS + P_COL;
 #pragma unroll
-                        for (int k = 0; k < static_cast<int>(KV_ROWS) / 16; ++k)          // 16 keys = 2 KB of V = 128 units of the descriptor's address field
-                            umma_bf16_ts(to, tp + k * 8, dv + 128 * k, idesc_o, static_cast<uint32_t>(k != 0));
-                    }
-                    umma_commit(o_bar(t));
+                for (int k = 0; k < static_cast<int>(KV_ROWS) / 16; ++k)          // 16 keys = 2 KB of V = 128 units of the descriptor's address field
+                    umma_bf16_ts(to, tp + k * 8, dv + 128 * k, idesc_o, static_cast<uint32_t>(k != 0));
+                umma_commit(o_bar(t));
+            };
+            int it = 0;
+            if (!pipe) {
+                for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
+                    mbar_wait(full_bar(it & 1), (it >> 1) & 1);
+                    tc_fence_after();
+                    SFB_TS(0);
+                    issue_s(0, it);
+                    SFB_TS(1);
+                    issue_s(1, it);
+                    SFB_TS(2);
+                    issue_pv(0, it);
+                    SFB_TS(3);
+                    issue_pv(1, it);
+                    SFB_TS(4);
+                    umma_commit(empty_bar(it & 1));                     // every MMA that reads this stage has been issued
                 }
-                umma_commit(empty_bar(s));                          // every MMA that reads this stage has been issued
+            } else {
+                // The two TMEM slots (tiles) run half a period apart: tile 1 of problem i-1 gets its P V and tile 1 of problem i its S while
+                // tile 0 of problem i is in its softmax, and vice versa - each tile's exp2 pass has the XU pipe to itself and the other tile's
+                // MMA / barrier latencies hide behind it.  Order per problem:  S(0,i)  PV(1,i-1)  S(1,i)  PV(0,i).  The phase offset is set
+                // once, by holding back the first S of tile 1 until tile 0 has finished its first softmax; nothing in the steady state changes it.
+                for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
+                    mbar_wait(full_bar(it & 1), (it >> 1) & 1);
+                    tc_fence_after();
+                    SFB_TS(0);
+                    issue_s(0, it);
+                    SFB_TS(1);
+                    if (it > 0) {
+                        issue_pv(1, it - 1);
+                        umma_commit(empty_bar((it - 1) & 1));
+                    } else {
+                        const long long t0 = clock64();
+                        while (clock64() - t0 < pipe) {}                 // `pipe` = initial stagger in clocks (~ half a period)
+                    }
+                    SFB_TS(2);
+                    issue_s(1, it);
+                    SFB_TS(3);
+                    issue_pv(0, it);
+                    SFB_TS(4);
+                }
+                if (it > 0) {
+                    issue_pv(1, it - 1);
+                    umma_commit(empty_bar((it - 1) & 1));
+                }
             }
         }
     } else {
@@ -237,13 +309,18 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const bool rows_live = t * 128 + (warp & 3) * 32 < Lq_eff;  // warp-uniform: a warp whose 32 rows are all padding only keeps the barriers in step
         const bool is_x = d.xq != nullptr && row == d.Lq;
         int it = 0;
+        // (head, inner, outer) of the NEXT problem are computed while this one waits for its P V: three integer divisions by run-time
+        // divisors (~430 clocks) were on the softmax warps' critical path at the top of every iteration
+        int nh = blockIdx.x % d.n_heads, ni = (blockIdx.x / d.n_heads) % d.n_inner, no = blockIdx.x / (d.n_heads * d.n_inner);
         for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
             if (!tile_live) continue;
-            const int ph = prob % d.n_heads, pi = (prob / d.n_heads) % d.n_inner, po = prob / (d.n_heads * d.n_inner);
+            const int ph = nh, pi = ni, po = no;
             // keys this row may see: all Lk (+ prefix); the extra query counts the prefix key in inner problem 0 only
             const int lk = (is_x && pi != 0) ? d.Lk : Lkp;
+            if ((warp & 3) == 0) SFB_TS(5 + 8 * t);
             mbar_wait(s_bar(t), it & 1);
             tc_fence_after();
+            if ((warp & 3) == 0) SFB_TS(6 + 8 * t);
             float inv = 0.f, mxs_keep = 0.f, sum_keep = 1.f;
             if (rows_live) {
                 uint32_t ra[32], rb[32];
@@ -251,17 +328,17 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 float mx = -INFINITY;
                 tmem_ld32(trow, ra);
                 tmem_ld_wait_dep(ra);
-#pragma unroll
+#pragma unroll 1          // rolled: the softmax loop body has to stay inside the instruction cache (see the header)
                 for (int c = 0; c < 6; c += 2) {
                     tmem_ld32(trow + (c + 1) * 32, rb);
-                    if ((c + 1) * 32 <= d.Lk) softmax_max32(ra, mx);
+                    if (kFull192 || (c + 1) * 32 <= d.Lk) softmax_max32(ra, mx);
                     else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (c * 32 + j < lk) mx = fmaxf(mx, __uint_as_float(ra[j]));
                     }
                     tmem_ld_wait_dep(rb);
                     if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
-                    if ((c + 2) * 32 <= d.Lk) softmax_max32(rb, mx);
+                    if (kFull192 || (c + 2) * 32 <= d.Lk) softmax_max32(rb, mx);
                     else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if ((c + 1) * 32 + j < lk) mx = fmaxf(mx, __uint_as_float(rb[j]));
@@ -271,15 +348,16 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 16; ++j) if (192 + j < lk) mx = fmaxf(mx, __uint_as_float(ra[j]));
                 const float mxs = mx * sl2;
+                if ((warp & 3) == 0) SFB_TS(7 + 8 * t);
                 // ---- pass 2: p = 2^(s*scale*log2e - max), row sum, P (bf16 pairs) written over the already consumed S columns
                 float sum = 0.f;
                 uint32_t pk[16];
                 tmem_ld32(trow, ra);
                 tmem_ld_wait_dep(ra);
-#pragma unroll
+#pragma unroll 1          // rolled: the softmax loop body has to stay inside the instruction cache (see the header)
                 for (int c = 0; c < 6; c += 2) {
                     tmem_ld32(trow + (c + 1) * 32, rb);
-                    if ((c + 1) * 32 <= d.Lk) softmax_exp32(ra, pk, sl2, mxs, sum);
+                    if (kFull192 || (c + 1) * 32 <= d.Lk) softmax_exp32(ra, pk, sl2, mxs, sum);
                     else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
@@ -292,7 +370,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     tmem_ld_wait_dep(rb);
                     tmem_st16(trow + P_COL + c * 16, pk);
                     if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
-                    if ((c + 2) * 32 <= d.Lk) softmax_exp32(rb, pk, sl2, mxs, sum);
+                    if (kFull192 || (c + 2) * 32 <= d.Lk) softmax_exp32(rb, pk, sl2, mxs, sum);
                     else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
@@ -322,10 +400,18 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
+            if ((warp & 3) == 0) SFB_TS(8 + 8 * t);
             if (lane == 0) mbar_arrive(p_bar(t));
+            // ---- while the tensor core forms O_t: next problem's indices, and the staging tile must be free again
+            {
+                const int np = prob + gridDim.x;
+                nh = np % d.n_heads, ni = (np / d.n_heads) % d.n_inner, no = np / (d.n_heads * d.n_inner);
+            }
+            if (tma_out && it > 0) mbar_wait(ofree_bar(t), (it - 1) & 1);    // the previous problem's store has finished reading the staging tile
             // ---- epilogue: O_t / sum -> bf16 -> one 128-byte row per thread
             mbar_wait(o_bar(t), it & 1);
             tc_fence_after();
+            if ((warp & 3) == 0) SFB_TS(9 + 8 * t);
             uint32_t o0[32], o1[32];
             if (rows_live) {
                 tmem_ld32(trow + O_COL, o0);
@@ -334,13 +420,18 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
+            if ((warp & 3) == 0) SFB_TS(10 + 8 * t);
             if (lane == 0) mbar_arrive(free_bar(t));                // TMEM columns of tile t may be overwritten by the next problem
             if (is_x) {       // softmax state of the extra query over this problem's keys (sfb_attention_merge_partials combines them)
                 float *xp = d.xpartial + ((static_cast<int64_t>(po) * d.n_heads + ph) * d.n_inner + pi) * (HD + 2);
-                xp[0] = mxs_keep, xp[1] = sum_keep;
+                float2 *xp2 = reinterpret_cast<float2 *>(xp);                 // entries are 66 floats apart: 8-byte aligned
+                xp2[0] = make_float2(mxs_keep, sum_keep);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) xp[2 + k] = __uint_as_float(o0[k]) * inv, xp[34 + k] = __uint_as_float(o1[k]) * inv;
-            } else if (rows_live && row < d.Lq) {
+                for (int k = 0; k < 16; ++k) {
+                    xp2[1 + k] = make_float2(__uint_as_float(o0[2 * k]) * inv, __uint_as_float(o0[2 * k + 1]) * inv);
+                    xp2[17 + k] = make_float2(__uint_as_float(o1[2 * k]) * inv, __uint_as_float(o1[2 * k + 1]) * inv);
+                }
+            } else if (!tma_out && rows_live && row < d.Lq) {
                 const int h = ph, i = pi, o = po;
                 uint4 *og = reinterpret_cast<uint4 *>(d.out + o * d.o_outer + i * d.o_inner + static_cast<int64_t>(row) * d.o_row + h * HD);
 #pragma unroll
@@ -355,6 +446,36 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                                            pack_bf16x2(__uint_as_float(o1[8 * k + 6]) * inv, __uint_as_float(o1[8 * k + 7]) * inv));
                 }
             }
+            if (tma_out) {
+                // Output rows leave through ONE TMA store per (problem, tile): a row-per-thread st.global of 128 bytes touches 32 different
+                // lines per instruction and kept the softmax warps ~1 800 clocks (clock64 stamps) before they could take the next problem.
+                // The tile's 4 warps write their rows into a 128B-swizzled staging tile (conflict-free per quarter-warp) and arrive on an
+                // mbarrier; the otherwise idle producer warp 11 hands the tile to the TMA unit.  The box of tile 1 has Lq - 128 rows, so
+                // padding rows and the extra-query row never reach memory.
+                const int rt = (warp & 3) * 32 + lane;                         // row inside the tile
+                if (rows_live) {
+                    uint8_t *orow = base_g + 2 * STAGE_BYTES_TC + t * O_STAGE_BYTES + rt * 128;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        *reinterpret_cast<uint4 *>(orow + ((k ^ (rt & 7)) << 4)) =
+                            make_uint4(pack_bf16x2(__uint_as_float(o0[8 * k]) * inv, __uint_as_float(o0[8 * k + 1]) * inv),
+                                       pack_bf16x2(__uint_as_float(o0[8 * k + 2]) * inv, __uint_as_float(o0[8 * k + 3]) * inv),
+                                       pack_bf16x2(__uint_as_float(o0[8 * k + 4]) * inv, __uint_as_float(o0[8 * k + 5]) * inv),
+                                       pack_bf16x2(__uint_as_float(o0[8 * k + 6]) * inv, __uint_as_float(o0[8 * k + 7]) * inv));
+                        *reinterpret_cast<uint4 *>(orow + (((4 + k) ^ (rt & 7)) << 4)) =
+                            make_uint4(pack_bf16x2(__uint_as_float(o1[8 * k]) * inv, __uint_as_float(o1[8 * k + 1]) * inv),
+                                       pack_bf16x2(__uint_as_float(o1[8 * k + 2]) * inv, __uint_as_float(o1[8 * k + 3]) * inv),
+                                       pack_bf16x2(__uint_as_float(o1[8 * k + 4]) * inv, __uint_as_float(o1[8 * k + 5]) * inv),
+                                       pack_bf16x2(__uint_as_float(o1[8 * k + 6]) * inv, __uint_as_float(o1[8 * k + 7]) * inv));
+                    }
+                }
+                if ((warp & 3) == 0) SFB_TS(20 + 2 * t);
+                fence_proxy_async_smem();                                      // generic-proxy writes -> visible to the TMA unit
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ofull_bar(t));
+                if ((warp & 3) == 0) SFB_TS(21 + 2 * t);
+            }
+            if ((warp & 3) == 0) SFB_TS(11 + 8 * t);
         }
     }
 
@@ -375,7 +496,10 @@ bool tc_supported(const Desc &d) {
 
 int launch_tc(const Desc &d, cudaStream_t st) {
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC));
+    if (attr_once.first()) {
+        SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC));
+        SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC));
+    }
     const int64_t n_prob = static_cast<int64_t>(d.n_outer) * d.n_inner * d.n_heads;
     SFB_CHECK_ARG(n_prob < (1ll << 31), "sfb_attention: too many problems");
     // TMA staging needs every problem's rows on one regular 2D grid: outer / inner strides must be whole rows
@@ -396,8 +520,27 @@ int launch_tc(const Desc &d, cudaStream_t st) {
         if (rc != SFB_OK) return rc;
         use_tma = 1;
     }
+    // output through TMA stores when the output rows also lie on one regular 2D grid
+    CUtensorMap to0, to1;
+    memset(&to0, 0, sizeof(to0)), memset(&to1, 0, sizeof(to1));
+    int tma_out = 0, oo = 0, oi = 0;
+    static const bool tma_out_enabled = !(getenv("SFB_ATTN_TMA_OUT") && atoi(getenv("SFB_ATTN_TMA_OUT")) == 0);
+    if (use_tma && tma_out_enabled && d.o_row > 0 && d.o_outer % d.o_row == 0 && d.o_inner % d.o_row == 0 && d.o_row >= d.n_heads * HD && d.o_row % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.Lq > 128) {
+        oo = static_cast<int>(d.o_outer / d.o_row), oi = static_cast<int>(d.o_inner / d.o_row);
+        const int64_t o_rows = static_cast<int64_t>(d.n_outer - 1) * oo + static_cast<int64_t>(d.n_inner - 1) * oi + d.Lq;
+        int rc = encode_tmap_bf16_2d(&to0, d.out, o_rows, d.n_heads * HD, d.o_row, 128, HD);
+        if (rc == SFB_OK) rc = encode_tmap_bf16_2d(&to1, d.out, o_rows, d.n_heads * HD, d.o_row, d.Lq - 128, HD);
+        if (rc != SFB_OK) return rc;
+        tma_out = 1;
+    }
     const unsigned grid = static_cast<unsigned>(n_prob < num_sms() ? n_prob : num_sms());
-    attn_space_tc_kernel<<<grid, kThreadsTc, SMEM_TC, st>>>(tq, tk, tv, d, static_cast<int>(n_prob), use_tma, qo, qi, ko, ki);
+    const int pipe = getenv("SFB_ATTN_PIPE") ? atoi(getenv("SFB_ATTN_PIPE")) : 3000;               // initial stagger in clocks; 0 = lock-step issue order (A/B aid)
+    long long *dbg = reinterpret_cast<long long *>(getenv("SFB_ATTN_DBG_PTR") ? strtoull(getenv("SFB_ATTN_DBG_PTR"), nullptr, 0) : 0ull);
+    if (d.Lk >= 192)
+        attn_space_tc_kernel<true><<<grid, kThreadsTc, SMEM_TC, st>>>(tq, tk, tv, to0, to1, tma_out, oo, oi, d, static_cast<int>(n_prob), use_tma, qo, qi, ko, ki, pipe, dbg);
+    else
+        attn_space_tc_kernel<false><<<grid, kThreadsTc, SMEM_TC, st>>>(tq, tk, tv, to0, to1, tma_out, oo, oi, d, static_cast<int>(n_prob), use_tma, qo, qi, ko, ki, pipe, dbg);
     SFB_CHECK_LAUNCH();
     return SFB_OK;
 }

@@ -130,15 +130,6 @@ __device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t cta_mask)
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
                  : "memory");
 }
-// TMA store of one shared-memory box (generic-proxy writes must be fenced with fence.proxy.async first); bulk-group completion
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0),
-                 "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the bit that distinguishes the two CTAs of a pair in a shared-window address
 
 // ------------------------------------------------------------------------------------------------ the kernel
