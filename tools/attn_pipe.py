@@ -10,7 +10,7 @@ from synchformer_b200 import ops  # noqa: E402
 
 D = 768
 NAMES = ['mma:full', 'mma:S0', 'mma:x', 'mma:S1|x', 'mma:end', 't0:preS', 't0:S', 't0:max', 't0:P', 't0:O', 't0:free', 't0:st', '-', 't1:preS', 't1:S', 't1:max', 't1:P', 't1:O',
-         't1:free', 't1:st', 't0:sts', 't0:bar', 't1:sts', 't1:bar']
+         't1:free', 't1:st', 't0:sts', 't0:arrive', 't1:sts', 't1:arrive']
 
 
 def attn(qkv, att, n):
