@@ -68,6 +68,24 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 
+// (head, inner, outer) of the problems a CTA visits: prob = first, first + stride, ...; advanced with two carries instead of three integer
+// divisions by run-time divisors per problem.  The divisions (3 x I2F / MUFU.RCP / F2I, on the XU pipe that one tile's exp2 pass saturates)
+// cost the softmax warps 430 - 790 clocks of critical path wherever they were written: the compiler sinks them next to their first use.
+struct ProblemIndex {
+    int h, i, o, step_h, step_i, step_o, n_heads, n_inner;
+    __device__ __forceinline__ ProblemIndex(int first, int stride, int n_heads_, int n_inner_) : n_heads(n_heads_), n_inner(n_inner_) {
+        h = first % n_heads, i = (first / n_heads) % n_inner, o = first / (n_heads * n_inner);
+        step_h = stride % n_heads, step_i = (stride / n_heads) % n_inner, step_o = stride / (n_heads * n_inner);
+    }
+    __device__ __forceinline__ void advance() {
+        h += step_h;
+        if (h >= n_heads) h -= n_heads, ++i;
+        i += step_i;
+        if (i >= n_inner) i -= n_inner, ++o;
+        o += step_o;
+    }
+};
+
 __device__ __forceinline__ void softmax_max32(const uint32_t (&r)[32], float &mx) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
@@ -94,15 +112,20 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                      const Desc d, int n_prob, int use_tma, int q_rows_outer, int q_rows_inner, int kv_rows_outer, int kv_rows_inner, int pipe,
                      long long *dbg) {
     extern __shared__ uint8_t smem_raw[];
-    // barriers: full[2] empty[2] | s_ready[2] p_ready[2] o_ready[2] tmem_free[2]
-    __shared__ __align__(8) uint64_t bars[16];      // ... | o_stage_full[2] o_stage_free[2] (output staging tiles <-> store-issuing warp)
+    // barriers: full_qk[2] empty_qk[2] | s_ready[2] p_ready[2] o_ready[2] tmem_free[2] | o_stage_full[2] o_stage_free[2] (output staging
+    // tiles <-> store-issuing warp) | full_v[2] empty_v[2].  Q / K and V of a stage are handed over separately: Q and K are dead as soon as
+    // S of tile 1 has been formed, V only after the last P V - with one barrier per stage the loads of problem i+1 could not start before the
+    // middle of problem i and arrived ~700 clocks late every period (clock64 stamps)
+    __shared__ __align__(8) uint64_t bars[20];
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_g = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bar0 = smem_u32(bars);
-    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };            // Q, K (+ CLS key row, extra query row)
     auto empty_bar = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto fullv_bar = [&](int s) { return bar0 + 8u * (16 + s); };    // V (+ CLS value row)
+    auto emptyv_bar = [&](int s) { return bar0 + 8u * (18 + s); };
     auto s_bar = [&](int t) { return bar0 + 8u * (4 + t); };
     auto p_bar = [&](int t) { return bar0 + 8u * (6 + t); };
     auto o_bar = [&](int t) { return bar0 + 8u * (8 + t); };
@@ -118,6 +141,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         for (int s = 0; s < 2; ++s) {
             mbar_init(full_bar(s), use_tma ? 2 : kProducerWarps);   // TMA: expect_tx arrive + the CLS-row warp; else 3 gather warps
             mbar_init(empty_bar(s), 1);
+            mbar_init(fullv_bar(s), use_tma ? 2 : kProducerWarps);
+            mbar_init(emptyv_bar(s), 1);
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(s_bar(t), 1);
@@ -152,8 +177,9 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             // tile sits on a softmax warp.  Tiles complete in the order 0, 1 within a problem.
             if (tma_out && lane == 0) {
                 int it = 0;
-                for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
-                    const int h = prob % d.n_heads, i = (prob / d.n_heads) % d.n_inner, o = prob / (d.n_heads * d.n_inner);
+                ProblemIndex pidx(blockIdx.x, gridDim.x, d.n_heads, d.n_inner);
+                for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it, pidx.advance()) {
+                    const int h = pidx.h, i = pidx.i, o = pidx.o;
                     for (int t = 0; t < n_tiles; ++t) {
                         mbar_wait(ofull_bar(t), it & 1);                 // the tile's 4 warps have written (and fenced) their rows
                         tma_store_2d(t == 0 ? &tm_o0 : &tm_o1, base + 2 * STAGE_BYTES_TC + t * O_STAGE_BYTES, h * HD, o * o_rows_outer + i * o_rows_inner + t * 128);
@@ -168,37 +194,49 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
         } else {
             int it = 0;
-            for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
+            ProblemIndex pidx(blockIdx.x, gridDim.x, d.n_heads, d.n_inner);
+            for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it, pidx.advance()) {
                 const int s = it & 1;
-                mbar_wait(empty_bar(s), ((it >> 1) & 1) ^ 1u);
-                const int h = prob % d.n_heads;
-                const int i = (prob / d.n_heads) % d.n_inner;
-                const int o = prob / (d.n_heads * d.n_inner);
+                const uint32_t empty_parity = ((it >> 1) & 1) ^ 1u;
+                mbar_wait(empty_bar(s), empty_parity);
+                const int h = pidx.h, i = pidx.i, o = pidx.o;
                 const uint32_t sQ = base + s * STAGE_BYTES_TC, sK = sQ + Q_BYTES, sV = sK + KV_BYTES;
                 const int64_t pre_base = o * d.prefix_outer + h * HD;
                 if (use_tma) {
                     if (pw == 0) {
                         if (lane == 0) {
-                            mbar_arrive_expect_tx(full_bar(s), static_cast<uint32_t>(d.Lq + 2 * d.Lk) * 128u);
+                            mbar_arrive_expect_tx(full_bar(s), static_cast<uint32_t>(d.Lq + d.Lk) * 128u);
                             tma_load_2d(sQ, &tm_q, full_bar(s), h * HD, o * q_rows_outer + i * q_rows_inner);
                             tma_load_2d(sK, &tm_k, full_bar(s), h * HD, o * kv_rows_outer + i * kv_rows_inner);
-                            tma_load_2d(sV, &tm_v, full_bar(s), h * HD, o * kv_rows_outer + i * kv_rows_inner);
+                            mbar_wait(emptyv_bar(s), empty_parity);
+                            mbar_arrive_expect_tx(fullv_bar(s), static_cast<uint32_t>(d.Lk) * 128u);
+                            tma_load_2d(sV, &tm_v, fullv_bar(s), h * HD, o * kv_rows_outer + i * kv_rows_inner);
                         }
                     } else {   // pw == 1: the CLS key / value row -> row d.Lk of the K / V tiles
-                        if (d.has_prefix && lane < 16) {
-                            const int cc = lane & 7, r = d.Lk;
-                            const uint32_t sw = r * 128 + ((cc ^ (r & 7)) << 4);
-                            cp_async16((lane < 8 ? sK : sV) + sw, (lane < 8 ? d.kp : d.vp) + pre_base + cc * 8);
+                        const int cc = lane & 7;
+                        if (d.has_prefix && lane < 8) {
+                            const int r = d.Lk;
+                            cp_async16(sK + r * 128 + ((cc ^ (r & 7)) << 4), d.kp + pre_base + cc * 8);
                         } else if (d.xq != nullptr && lane >= 16 && lane < 24) {      // fused extra query -> query row Lq
-                            const int cc = lane & 7, r = d.Lq;
+                            const int r = d.Lq;
                             cp_async16(sQ + r * 128 + ((cc ^ (r & 7)) << 4), d.xq + o * d.xq_outer + h * HD + cc * 8);
                         }
                         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_bar(s));
+                        mbar_wait(emptyv_bar(s), empty_parity);
+                        if (d.has_prefix && lane >= 8 && lane < 16) {
+                            const int r = d.Lk;
+                            cp_async16(sV + r * 128 + ((cc ^ (r & 7)) << 4), d.vp + pre_base + cc * 8);
+                        }
+                        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(fullv_bar(s));
                     }
                 } else {
+                    mbar_wait(emptyv_bar(s), empty_parity);
                     const int ptid = threadIdx.x - 9 * 32;          // 0..95
                     const __nv_bfloat16 *qg = d.q + o * d.q_outer + i * d.q_inner + h * HD;
                     for (int c = ptid; c < d.Lq * 8; c += kProducerWarps * 32) {
@@ -221,7 +259,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
                     fence_proxy_async_smem();               // generic-proxy writes -> visible to tcgen05.mma (async proxy)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(full_bar(s));
+                    if (lane == 0) mbar_arrive(full_bar(s)), mbar_arrive(fullv_bar(s));
                 }
             }
         }
@@ -256,6 +294,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             if (!pipe) {
                 for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
                     mbar_wait(full_bar(it & 1), (it >> 1) & 1);
+                    mbar_wait(fullv_bar(it & 1), (it >> 1) & 1);
                     tc_fence_after();
                     SFB_TS(0);
                     issue_s(0, it);
@@ -267,6 +306,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     issue_pv(1, it);
                     SFB_TS(4);
                     umma_commit(empty_bar(it & 1));                     // every MMA that reads this stage has been issued
+                    umma_commit(emptyv_bar(it & 1));
                 }
             } else {
                 // The two TMEM slots (tiles) run half a period apart: tile 1 of problem i-1 gets its P V and tile 1 of problem i its S while
@@ -281,20 +321,23 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     SFB_TS(1);
                     if (it > 0) {
                         issue_pv(1, it - 1);
-                        umma_commit(empty_bar((it - 1) & 1));
+                        umma_commit(emptyv_bar((it - 1) & 1));           // V of problem i-1 is dead
                     } else {
                         const long long t0 = clock64();
                         while (clock64() - t0 < pipe) {}                 // `pipe` = initial stagger in clocks (~ half a period)
                     }
                     SFB_TS(2);
                     issue_s(1, it);
+                    umma_commit(empty_bar(it & 1));                      // Q, K of problem i are dead once both S tiles exist
                     SFB_TS(3);
+                    mbar_wait(fullv_bar(it & 1), (it >> 1) & 1);
+                    tc_fence_after();
                     issue_pv(0, it);
                     SFB_TS(4);
                 }
                 if (it > 0) {
                     issue_pv(1, it - 1);
-                    umma_commit(empty_bar((it - 1) & 1));
+                    umma_commit(emptyv_bar((it - 1) & 1));
                 }
             }
         }
@@ -309,12 +352,10 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const bool rows_live = t * 128 + (warp & 3) * 32 < Lq_eff;  // warp-uniform: a warp whose 32 rows are all padding only keeps the barriers in step
         const bool is_x = d.xq != nullptr && row == d.Lq;
         int it = 0;
-        // (head, inner, outer) of the NEXT problem are computed while this one waits for its P V: three integer divisions by run-time
-        // divisors (~430 clocks) were on the softmax warps' critical path at the top of every iteration
-        int nh = blockIdx.x % d.n_heads, ni = (blockIdx.x / d.n_heads) % d.n_inner, no = blockIdx.x / (d.n_heads * d.n_inner);
+        ProblemIndex pidx(blockIdx.x, gridDim.x, d.n_heads, d.n_inner);
         for (int prob = blockIdx.x; prob < n_prob; prob += gridDim.x, ++it) {
             if (!tile_live) continue;
-            const int ph = nh, pi = ni, po = no;
+            const int ph = pidx.h, pi = pidx.i, po = pidx.o;
             // keys this row may see: all Lk (+ prefix); the extra query counts the prefix key in inner problem 0 only
             const int lk = (is_x && pi != 0) ? d.Lk : Lkp;
             if ((warp & 3) == 0) SFB_TS(5 + 8 * t);
@@ -403,10 +444,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             if ((warp & 3) == 0) SFB_TS(8 + 8 * t);
             if (lane == 0) mbar_arrive(p_bar(t));
             // ---- while the tensor core forms O_t: next problem's indices, and the staging tile must be free again
-            {
-                const int np = prob + gridDim.x;
-                nh = np % d.n_heads, ni = (np / d.n_heads) % d.n_inner, no = np / (d.n_heads * d.n_inner);
-            }
+            pidx.advance();
             if (tma_out && it > 0) mbar_wait(ofree_bar(t), (it - 1) & 1);    // the previous problem's store has finished reading the staging tile
             // ---- epilogue: O_t / sum -> bf16 -> one 128-byte row per thread
             mbar_wait(o_bar(t), it & 1);
