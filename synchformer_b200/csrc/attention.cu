@@ -638,7 +638,7 @@ extern "C" int sfb_attention_extra_supported(const sfb_attn_desc *desc) {
     if (getenv("SFB_ATTN_TC") && atoi(getenv("SFB_ATTN_TC")) == 0) return 0;
     if ((reinterpret_cast<uintptr_t>(desc->q_extra) & 15) != 0 || desc->q_extra_outer % 8 != 0) return 0;
     Desc d = {};
-    d.Lq = desc->Lq, d.Lk = desc->Lk, d.has_prefix = desc->k_prefix != nullptr;
+    d.Lq = desc->Lq, d.Lk = desc->Lk, d.has_prefix = desc->k_prefix != nullptr, d.scale = desc->scale;
     return tc_supported(d) && desc->Lq < 256 ? 1 : 0;     // the extra query occupies query row Lq of the second 128-row tile
 }
 

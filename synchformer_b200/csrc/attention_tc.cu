@@ -58,6 +58,7 @@ constexpr uint32_t STAGE_BYTES_TC = Q_BYTES + 2 * KV_BYTES;             // 84 KB
 constexpr uint32_t O_STAGE_BYTES = 128 * 128;                           // one tile's bf16 output rows (128 rows x 64 dims), 128B-swizzled
 constexpr uint32_t SMEM_TC = 2 * STAGE_BYTES_TC + 2 * O_STAGE_BYTES + 1024;
 constexpr uint32_t TILE_COLS = 256, P_COL = 0, O_COL = 128;
+constexpr float kMaxAboveRef = 100.f;   // single-pass softmax: how far (log2) a row's maximum may lie above its reference value
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -86,9 +87,14 @@ struct ProblemIndex {
     }
 };
 
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+    float y;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+    return y;
+}
 __device__ __forceinline__ void softmax_max32(const uint32_t (&r)[32], float &mx) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+    for (int j = 0; j < 32; j += 2) mx = max3f(mx, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
 }
 // 32 scores -> 16 packed bf16 probability pairs, running sum
 __device__ __forceinline__ void softmax_exp32(const uint32_t (&r)[32], uint32_t (&pk)[16], float sl2, float mxs, float &sum) {
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
 attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                      const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1, int tma_out, int o_rows_outer, int o_rows_inner,
                      const Desc d, int n_prob, int use_tma, int q_rows_outer, int q_rows_inner, int kv_rows_outer, int kv_rows_inner, int pipe,
-                     long long *dbg) {
+                     uint32_t *__restrict__ flags, long long *dbg) {
     extern __shared__ uint8_t smem_raw[];
     // barriers: full_qk[2] empty_qk[2] | s_ready[2] p_ready[2] o_ready[2] tmem_free[2] | o_stage_full[2] o_stage_free[2] (output staging
     // tiles <-> store-issuing warp) | full_v[2] empty_v[2].  Q / K and V of a stage are handed over separately: Q and K are dead as soon as
@@ -363,38 +369,31 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             tc_fence_after();
             if ((warp & 3) == 0) SFB_TS(6 + 8 * t);
             float inv = 0.f, mxs_keep = 0.f, sum_keep = 1.f;
+            bool redo = false;
             if (rows_live) {
                 uint32_t ra[32], rb[32];
-                // ---- pass 1: row maximum.  Columns 0..191 in six x32 loads (next load in flight while this one is reduced), then 192..207
-                float mx = -INFINITY;
-                tmem_ld32(trow, ra);
-                tmem_ld_wait_dep(ra);
-#pragma unroll 1          // rolled: the softmax loop body has to stay inside the instruction cache (see the header)
-                for (int c = 0; c < 6; c += 2) {
-                    tmem_ld32(trow + (c + 1) * 32, rb);
-                    if (kFull192 || (c + 1) * 32 <= d.Lk) softmax_max32(ra, mx);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (c * 32 + j < lk) mx = fmaxf(mx, __uint_as_float(ra[j]));
-                    }
-                    tmem_ld_wait_dep(rb);
-                    if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
-                    if (kFull192 || (c + 2) * 32 <= d.Lk) softmax_max32(rb, mx);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if ((c + 1) * 32 + j < lk) mx = fmaxf(mx, __uint_as_float(rb[j]));
-                    }
-                    tmem_ld_wait_dep(ra);
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) if (192 + j < lk) mx = fmaxf(mx, __uint_as_float(ra[j]));
-                const float mxs = mx * sl2;
-                if ((warp & 3) == 0) SFB_TS(7 + 8 * t);
-                // ---- pass 2: p = 2^(s*scale*log2e - max), row sum, P (bf16 pairs) written over the already consumed S columns
-                float sum = 0.f;
+                // ---- ONE pass over the scores: p = 2^(s*scale*log2e - ref), row sum, P (bf16 pairs) written over the already consumed S
+                // columns.  `ref` is not the row maximum - finding that first is a second sweep over TMEM, 980 of the 6 000 clocks of a
+                // problem - but the maximum of the first 32 scores.  Softmax is invariant to the reference as long as nothing overflows,
+                // so the true maximum is formed NEXT TO the exp2s (FMNMX3s, hidden under the XU-bound exp2s; no branch, nothing waits for
+                // them) and examined afterwards: a row whose maximum exceeds its reference by less than 2^100 has P <= 2^100 and an fp32
+                // row sum <= 208 * 2^100 - exact, and >= 1 because the reference is one of the row's own scores.  A row beyond that (never
+                // seen outside the adversarial unit test) is reported in `flags` and recomputed by attn_space_fixup_kernel afterwards.
+                float sum = 0.f, run;
                 uint32_t pk[16];
                 tmem_ld32(trow, ra);
                 tmem_ld_wait_dep(ra);
+                {
+                    float m0 = -INFINITY;
+                    if (kFull192 || 32 <= d.Lk) softmax_max32(ra, m0);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < lk) m0 = fmaxf(m0, __uint_as_float(ra[j]));
+                    }
+                    run = m0;
+                }
+                const float mxs = run * sl2;
+                if ((warp & 3) == 0) SFB_TS(7 + 8 * t);
 #pragma unroll 1          // rolled: the softmax loop body has to stay inside the instruction cache (see the header)
                 for (int c = 0; c < 6; c += 2) {
                     tmem_ld32(trow + (c + 1) * 32, rb);
@@ -411,36 +410,56 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     tmem_ld_wait_dep(rb);
                     tmem_st16(trow + P_COL + c * 16, pk);
                     if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
-                    if (kFull192 || (c + 2) * 32 <= d.Lk) softmax_exp32(rb, pk, sl2, mxs, sum);
-                    else {
+                    if (kFull192 || (c + 2) * 32 <= d.Lk) {
+                        softmax_max32(rb, run);
+                        softmax_exp32(rb, pk, sl2, mxs, sum);
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const float p0 = (c + 1) * 32 + j < lk ? ex2f(fmaf(__uint_as_float(rb[j]), sl2, -mxs)) : 0.f;
-                            const float p1 = (c + 1) * 32 + j + 1 < lk ? ex2f(fmaf(__uint_as_float(rb[j + 1]), sl2, -mxs)) : 0.f;
+                            const bool l0 = (c + 1) * 32 + j < lk, l1 = (c + 1) * 32 + j + 1 < lk;
+                            if (l0) run = fmaxf(run, __uint_as_float(rb[j]));
+                            if (l1) run = fmaxf(run, __uint_as_float(rb[j + 1]));
+                            const float p0 = l0 ? ex2f(fmaf(__uint_as_float(rb[j]), sl2, -mxs)) : 0.f;
+                            const float p1 = l1 ? ex2f(fmaf(__uint_as_float(rb[j + 1]), sl2, -mxs)) : 0.f;
                             sum += p0 + p1;
                             pk[j >> 1] = pack_bf16x2(p0, p1);
                         }
                     }
                     tmem_ld_wait_dep(ra);
                     tmem_st16(trow + P_COL + (c + 1) * 16, pk);
+                    // the chunk now in `ra` (32 columns, or the 16-column tail after the last round) joins the running maximum
+                    if (c + 2 < 6) {
+                        if (kFull192 || (c + 3) * 32 <= d.Lk) softmax_max32(ra, run);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if ((c + 2) * 32 + j < lk) run = fmaxf(run, __uint_as_float(ra[j]));
+                        }
+                    }
                 }
                 {
                     uint32_t pt[8];
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
-                        const float p0 = 192 + j < lk ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
-                        const float p1 = 192 + j + 1 < lk ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
+                        const bool l0 = 192 + j < lk, l1 = 192 + j + 1 < lk;
+                        if (l0) run = fmaxf(run, __uint_as_float(ra[j]));
+                        if (l1) run = fmaxf(run, __uint_as_float(ra[j + 1]));
+                        const float p0 = l0 ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
+                        const float p1 = l1 ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
                         sum += p0 + p1;
                         pt[j >> 1] = pack_bf16x2(p0, p1);
                     }
                     tmem_st8(trow + P_COL + 96, pt);
                 }
+                redo = !(fmaf(run, sl2, -mxs) <= kMaxAboveRef);      // also true for a NaN score row: recomputed the slow way, still NaN
                 tmem_st_wait();
                 inv = 1.0f / sum;
                 mxs_keep = mxs, sum_keep = sum;
             }
             tc_fence_before();
-            __syncwarp();
+            {
+                const uint32_t redo_rows = __ballot_sync(0xffffffffu, redo);       // always written: the fix-up kernel needs no memset
+                if (lane == 0) flags[static_cast<int64_t>(prob) * 8 + warp] = redo_rows;
+            }
             if ((warp & 3) == 0) SFB_TS(8 + 8 * t);
             if (lane == 0) mbar_arrive(p_bar(t));
             // ---- while the tensor core forms O_t: next problem's indices, and the staging tile must be free again
@@ -525,11 +544,61 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
 }
 
+
+// Rows the single-pass softmax reported in `flags` (their scores rise more than 2^kMaxAboveRef above the first 32 scores): recomputed from
+// the operands in global memory with an online softmax, one warp per row, and written over what the tensor-core kernel stored - the
+// output row, or the partial state of the fused extra query (which the merge kernel reads afterwards).  Word w of a problem's 8 flag words
+// covers query rows 32 w .. 32 w + 31.  With no row reported (always, outside the unit test) this kernel reads 32 bytes per problem.
+__global__ void __launch_bounds__(256) attn_space_fixup_kernel(const Desc d, const uint32_t *__restrict__ flags, int n_prob, int n_words) {
+    const int lane = threadIdx.x & 31;
+    const float sl2 = d.scale * 1.4426950408889634f;
+    for (int prob = blockIdx.x * 8 + (threadIdx.x >> 5); prob < n_prob; prob += gridDim.x * 8) {
+        const uint32_t mine = lane < n_words ? flags[static_cast<int64_t>(prob) * 8 + lane] : 0u;
+        if (!__any_sync(0xffffffffu, mine != 0u)) continue;
+        const int h = prob % d.n_heads, i = (prob / d.n_heads) % d.n_inner, o = prob / (d.n_heads * d.n_inner);
+        for (int w = 0; w < n_words; ++w) {
+            uint32_t rows = __shfl_sync(0xffffffffu, mine, w);
+            while (rows != 0u) {
+                const int r = w * 32 + __ffs(rows) - 1;
+                rows &= rows - 1;
+                const bool is_x = d.xq != nullptr && r == d.Lq;
+                if (r > d.Lq || (r == d.Lq && !is_x)) continue;                    // padding rows are never reported; belt and braces
+                const __nv_bfloat16 *qp = is_x ? d.xq + o * d.xq_outer + h * HD : d.q + o * d.q_outer + i * d.q_inner + static_cast<int64_t>(r) * d.q_row + h * HD;
+                const float2 q = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(qp + 2 * lane));
+                const int64_t kv_base = o * d.kv_outer + i * d.kv_inner + h * HD + 2 * lane;
+                const bool with_prefix = d.has_prefix && (!is_x || i == 0);       // the extra query counts the prefix key once, in inner problem 0
+                float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+                for (int j = 0; j < d.Lk + (with_prefix ? 1 : 0); ++j) {
+                    const bool pre = j == d.Lk;
+                    const int64_t off = pre ? o * d.prefix_outer + h * HD + 2 * lane : kv_base + static_cast<int64_t>(j) * d.kv_row;
+                    const float2 k = unpack_bf16x2(*reinterpret_cast<const uint32_t *>((pre ? d.kp : d.k) + off));
+                    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t *>((pre ? d.vp : d.v) + off));
+                    const float sc = warp_sum(fmaf(q.x, k.x, q.y * k.y)) * sl2;
+                    const float m_new = fmaxf(m, sc);
+                    const float corr = exp2f(m - m_new), p = exp2f(sc - m_new);
+                    l = fmaf(l, corr, p), a0 = fmaf(a0, corr, p * v.x), a1 = fmaf(a1, corr, p * v.y);
+                    m = m_new;
+                }
+                const float inv = 1.0f / l;
+                if (is_x) {
+                    float *xp = d.xpartial + ((static_cast<int64_t>(o) * d.n_heads + h) * d.n_inner + i) * (HD + 2);
+                    if (lane == 0) xp[0] = m, xp[1] = l;
+                    xp[2 + 2 * lane] = a0 * inv, xp[3 + 2 * lane] = a1 * inv;
+                } else {
+                    __nv_bfloat16 *op = d.out + o * d.o_outer + i * d.o_inner + static_cast<int64_t>(r) * d.o_row + h * HD;
+                    *reinterpret_cast<uint32_t *>(op + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 bool tc_supported(const Desc &d) {
     const int Lkp = d.Lk + d.has_prefix;
-    return d.Lq > 128 && d.Lq <= 256 && Lkp >= 16 && Lkp <= static_cast<int>(KV_ROWS);
+    // scale > 0: the single-pass softmax compares chunk maxima of the raw scores with its reference value
+    return d.Lq > 128 && d.Lq <= 256 && Lkp >= 16 && Lkp <= static_cast<int>(KV_ROWS) && d.scale > 0.f;
 }
 
 int launch_tc(const Desc &d, cudaStream_t st) {
@@ -575,11 +644,32 @@ int launch_tc(const Desc &d, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>(n_prob < num_sms() ? n_prob : num_sms());
     const int pipe = getenv("SFB_ATTN_PIPE") ? atoi(getenv("SFB_ATTN_PIPE")) : 3000;               // initial stagger in clocks; 0 = lock-step issue order (A/B aid)
     long long *dbg = reinterpret_cast<long long *>(getenv("SFB_ATTN_DBG_PTR") ? strtoull(getenv("SFB_ATTN_DBG_PTR"), nullptr, 0) : 0ull);
+    // per-launch flag words of the single-pass softmax (8 per problem), stream-ordered so that concurrent launches on other streams cannot
+    // share them; the pool keeps the block, so this is a free-list pop after the first call
+    static PerDeviceOnce pool_once;
+    if (pool_once.first()) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        uint64_t keep = UINT64_MAX;
+        SFB_CHECK_CUDA(cudaGetDevice(&dev));
+        SFB_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        SFB_CHECK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    uint32_t *flags = nullptr;
+    SFB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&flags), static_cast<size_t>(n_prob) * 8 * sizeof(uint32_t), st));
     if (d.Lk >= 192)
-        attn_space_tc_kernel<true><<<grid, kThreadsTc, SMEM_TC, st>>>(tq, tk, tv, to0, to1, tma_out, oo, oi, d, static_cast<int>(n_prob), use_tma, qo, qi, ko, ki, pipe, dbg);
+        attn_space_tc_kernel<true><<<grid, kThreadsTc, SMEM_TC, st>>>(tq, tk, tv, to0, to1, tma_out, oo, oi, d, static_cast<int>(n_prob), use_tma, qo, qi, ko, ki, pipe, flags, dbg);
     else
-        attn_space_tc_kernel<false><<<grid, kThreadsTc, SMEM_TC, st>>>(tq, tk, tv, to0, to1, tma_out, oo, oi, d, static_cast<int>(n_prob), use_tma, qo, qi, ko, ki, pipe, dbg);
-    SFB_CHECK_LAUNCH();
+        attn_space_tc_kernel<false><<<grid, kThreadsTc, SMEM_TC, st>>>(tq, tk, tv, to0, to1, tma_out, oo, oi, d, static_cast<int>(n_prob), use_tma, qo, qi, ko, ki, pipe, flags, dbg);
+    cudaError_t launch_err = cudaGetLastError();
+    if (launch_err == cudaSuccess) {
+        const int64_t want = (n_prob + 7) / 8;
+        const unsigned fix_grid = static_cast<unsigned>(want < 4 * num_sms() ? want : 4 * num_sms());
+        attn_space_fixup_kernel<<<fix_grid, 256, 0, st>>>(d, flags, static_cast<int>(n_prob), 4 * ((d.Lq + 127) / 128));
+        launch_err = cudaGetLastError();
+    }
+    cudaFreeAsync(flags, st);
+    SFB_CHECK_CUDA(launch_err);
     return SFB_OK;
 }
 

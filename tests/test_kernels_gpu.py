@@ -254,6 +254,48 @@ def test_space_attention_softmax_reference_value(cuda_device, q_gain, k_gain):
     assert rel_l2(got, ref) < 8e-3, (q_gain, k_gain, rel_l2(got, ref))
 
 
+@pytest.mark.parametrize('direction', [1.0, -1.0])
+def test_space_attention_single_pass_softmax_raises_its_reference(cuda_device, direction):
+    """The tcgen05 space-attention kernel exponentiates against a reference value taken from the first 32 keys and raises it when a later
+    chunk of keys exceeds it by more than 2^64 (already stored probabilities are rescaled by an exact power of two).  Keys whose scores
+    grow with the key index (every chunk, the 16-key tail and the CLS prefix key trigger a raise) or fall with it (no raise at all), with a
+    step of ~90 log2 units per 32 keys, against fp32 torch."""
+    from synchformer_b200 import ops
+    n, D = 1, 768
+    g = torch.Generator(device='cuda').manual_seed(11)
+    raw = torch.randn(n * 1569, 3 * D, device='cuda', generator=g)
+    u = torch.randn(12, 64, device='cuda', generator=g)
+    u = u / u.norm(dim=1, keepdim=True)
+    # q = a u + noise, k_j = ramp(j) u + noise: score ~ a ramp(j) / 8; the ramp also differs per frame and is largest for the CLS row
+    pos = torch.arange(1569, device='cuda', dtype=torch.float32)
+    ramp = direction * ((pos - 1) % 196) * 1.0
+    ramp[0] = direction * 230.0
+    raw[:, :D] = raw[:, :D] + 125.0 * u.reshape(1, D)
+    raw[:, D:2 * D] = raw[:, D:2 * D] * 0.5 + ramp[:, None] * u.reshape(1, D) * 0.125
+    qkv = _bf(raw)
+    att = torch.zeros(n * 1569, D, device='cuda', dtype=torch.bfloat16)
+    row, seg = 3 * D, 1569 * 3 * D
+    t = qkv.float().view(n, 1569, 3, 12, 64)
+    q, k, v = t[:, :, 0].permute(0, 2, 1, 3), t[:, :, 1].permute(0, 2, 1, 3), t[:, :, 2].permute(0, 2, 1, 3)
+    q_, k_, v_ = [x[:, :, 1:].reshape(n, 12, 8, 196, 64) for x in (q, k, v)]
+    kk = torch.cat([k[:, :, :1].unsqueeze(2).expand(n, 12, 8, 1, 64), k_], 3)
+    vv = torch.cat([v[:, :, :1].unsqueeze(2).expand(n, 12, 8, 1, 64), v_], 3)
+    logits = torch.einsum('bhfqd,bhfkd->bhfqk', q_, kk) * 0.125 * 1.4426950408889634
+    spread = (logits[..., 33:].amax(-1) - logits[..., 1:33].amax(-1))             # keys 0..31 of the kernel's order are columns 1..32 here
+    if direction > 0:
+        assert spread.min() > 64.0 * 2, spread.min()                             # every row has to raise its reference, several times
+    else:
+        assert spread.max() < 0.0
+    ref = _ref_attention(q_, kk, vv, 0.125).reshape(n, 12, 1568, 64)
+    ops.attention(qkv[1:], qkv[1:, D:], qkv[1:, 2 * D:], att[1:], q_strides=(seg, 196 * row, row), kv_strides=(seg, 196 * row, row),
+                  o_strides=(1569 * D, 196 * D, D), n_outer=n, n_inner=8, n_heads=12, head_dim=64, Lq=196, Lk=196, scale=0.125,
+                  k_prefix=qkv[:, D:], v_prefix=qkv[:, 2 * D:], prefix_outer=seg)
+    torch.cuda.synchronize()
+    got = att.view(n, 1569, 12, 64)[:, 1:].permute(0, 2, 1, 3).float()
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, ref) < 8e-3, rel_l2(got, ref)
+
+
 @pytest.mark.parametrize('impl', [pytest.param(0, id='tc'), pytest.param(1, id='simple')])
 @pytest.mark.parametrize('L,heads,hd', [(74, 12, 64), (198, 8, 96), (114, 8, 96), (30, 8, 96), (16, 12, 64), (17, 12, 64)])
 def test_plain_self_attention(cuda_device, impl, L, heads, hd):
