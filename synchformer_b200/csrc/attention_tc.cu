@@ -11,14 +11,15 @@
 //   warp 8      MMA issuer  S_t = Q_t K^T   (2 row tiles t of 128 queries; 4 x tcgen05.mma M128 N208 K16, operands from smem)
 //                           O_t = P_t V     (13 x tcgen05.mma M128 N64 K16, A = P_t read from TMEM, B = V as an MN-major operand:
 //                           the [key][64 dims] rows are used as they are, no transpose)
-//   warps 0-7   softmax     thread = query row (TMEM lane).  Two passes over the fp32 scores with software-pipelined tcgen05.ld
-//                           (row max, then exp2 / row sum), P written back over S as packed bf16 with tcgen05.st, then the O epilogue:
-//                           tcgen05.ld, 1/sum, bf16, one 128-byte row store per thread.
-// TMEM (512 columns): tile t owns columns [256t, 256t+208): S fp32 there; P (bf16 pairs) re-uses columns [0,104) of the same
-// range as the softmax consumes S; O accumulates in columns [128,192) once S is dead.
+//   warps 0-7   softmax     thread = query row (TMEM lane).  One sweep over the fp32 scores with software-pipelined tcgen05.ld
+//                           (exp2 against a reference value, row sum, running maximum), P written back as packed bf16 with
+//                           tcgen05.st, then the O epilogue: tcgen05.ld, 1/sum, bf16, rows into a swizzled staging tile that leaves
+//                           through one TMA store per tile (issued by warp 11).
+// TMEM (512 columns): tile t owns columns [256t, 256t+248): S fp32 in the first 208; P (bf16 pairs) of keys 0..127 re-uses columns
+// [0,64) as the softmax consumes S, P of keys 128..207 goes to the spare columns [208,248), O accumulates in columns [64,128).
 // Nothing touches HBM between the qkv activations and the attention output.
 //
-// What bounds it (round 2, clock64 phase stamps of one CTA, tools/attn_pipe.py; 1.76 -> 1.19 ms per launch at 512 segments):
+// What bounds it (round 2, clock64 phase stamps of one CTA, tools/attn_pipe.py; 1.76 -> 1.09 ms per launch at 512 segments):
 //   * the MMA phases are short bursts whose cost is issue + ~400 clocks of commit latency, not tensor work: fully unrolled issue sequences
 //     with constant-offset descriptors (56 instead of 150 clocks per tcgen05.mma, tools/ubench/mma_cost.cu);
 //   * the two tiles of a problem must not run in lock-step: issue order S(0,i) PV(1,i-1) S(1,i) PV(0,i) puts one tile's exp2 pass (XU
@@ -29,8 +30,18 @@
 //   * three integer divisions by run-time divisors at the top of every iteration (~430 clocks) moved behind the wait for P V;
 //   * the loop body of the softmax warps has to fit the instruction cache: the masked variants of the chunk code are compiled out for
 //     Lk >= 192 and the chunk loops are rolled (89 KB -> 58 KB of SASS: 1.37 -> 1.19 ms on its own).
-// Tried and measured, not adopted: a single-pass softmax whose reference value is the Cauchy-Schwarz bound |q| max|k| scale (the max
-// pass is only 8 % of the time; the norms from shared memory plus a named barrier cost 30 %).
+//   * the loads of problem i+1 must not wait for the last P V of problem i-1: Q / K and V of a stage are handed back on separate barriers
+//     (Q and K are dead once both S tiles exist), 1.19 -> 1.13 ms;
+//   * softmax in ONE sweep over TMEM (reference value = maximum of the first 32 scores, the true maximum tracked beside the exp2s, rows
+//     that rise more than 2^100 above their reference flagged and recomputed by attn_space_fixup_kernel) and the first 8 of the 13 P V
+//     instructions issued while the scores of keys 128.. are still being exponentiated (P / O laid out so that O never overlaps live
+//     scores): 1.13 -> 1.09 ms.  What is left is the XU pipe: 2 x 32 rows x 208 exp2 per sub-partition and problem at ~10.5 clocks per
+//     MUFU.EX2 warp instruction (tools/ubench/xu_pipe.cu) = 4 400 of the ~5 800 clocks of a problem.
+// Tried and measured, not adopted: a single-pass softmax whose reference value is the Cauchy-Schwarz bound |q| max|k| scale (the norms from
+// shared memory plus a named barrier cost 30 %); a lazily raised reference with an in-line rescale branch per chunk (drains the XU pipe at
+// every chunk: 1.24 ms) or a retry loop around the chunk (spills: 2.1 ms); 3 of 8 exp2 as a degree-3 polynomial on the FMA / ALU pipes
+// (FA4 style; 7.5e-5 relative error): the polynomial costs ~14 clocks per warp and element against 10.5 for MUFU.EX2 and the mix runs at
+// 1.25 ms - this pass is bound by issue slots and dependent-instruction latency of two co-resident warps as much as by the XU pipe.
 #include <stdlib.h>
 #include <string.h>
 
@@ -57,7 +68,11 @@ constexpr uint32_t KV_BYTES = KV_ROWS * 128;                            // 26 KB
 constexpr uint32_t STAGE_BYTES_TC = Q_BYTES + 2 * KV_BYTES;             // 84 KB
 constexpr uint32_t O_STAGE_BYTES = 128 * 128;                           // one tile's bf16 output rows (128 rows x 64 dims), 128B-swizzled
 constexpr uint32_t SMEM_TC = 2 * STAGE_BYTES_TC + 2 * O_STAGE_BYTES + 1024;
-constexpr uint32_t TILE_COLS = 256, P_COL = 0, O_COL = 128;
+// TMEM columns of a tile: S fp32 in [0,208).  P (bf16 pairs, 16 columns per 32 keys) of keys 0..127 over the dead S columns [0,64), P of keys
+// 128..207 in the spare columns [208,248), O in [64,128): the first 8 of the 13 P V instructions can be issued - and accumulate into O - while
+// the softmax is still reading the scores of keys 128.. from columns [128,208)
+constexpr uint32_t TILE_COLS = 256, P_COL = 0, PB_COL = 208, O_COL = 64;
+constexpr int kKeysA = 128;              // keys covered by the first P V burst
 constexpr float kMaxAboveRef = 100.f;   // single-pass softmax: how far (log2) a row's maximum may lie above its reference value
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
@@ -122,7 +137,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     // tiles <-> store-issuing warp) | full_v[2] empty_v[2].  Q / K and V of a stage are handed over separately: Q and K are dead as soon as
     // S of tile 1 has been formed, V only after the last P V - with one barrier per stage the loads of problem i+1 could not start before the
     // middle of problem i and arrived ~700 clocks late every period (clock64 stamps)
-    __shared__ __align__(8) uint64_t bars[20];
+    __shared__ __align__(8) uint64_t bars[22];         // ... | p_late_ready[2]
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -133,7 +148,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     auto fullv_bar = [&](int s) { return bar0 + 8u * (16 + s); };    // V (+ CLS value row)
     auto emptyv_bar = [&](int s) { return bar0 + 8u * (18 + s); };
     auto s_bar = [&](int t) { return bar0 + 8u * (4 + t); };
-    auto p_bar = [&](int t) { return bar0 + 8u * (6 + t); };
+    auto p_bar = [&](int t) { return bar0 + 8u * (6 + t); };           // P of keys 0..127 stored
+    auto pb_bar = [&](int t) { return bar0 + 8u * (20 + t); };         // P of the remaining keys stored
     auto o_bar = [&](int t) { return bar0 + 8u * (8 + t); };
     auto free_bar = [&](int t) { return bar0 + 8u * (10 + t); };
     auto ofull_bar = [&](int t) { return bar0 + 8u * (12 + t); };
@@ -153,6 +169,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         for (int t = 0; t < 2; ++t) {
             mbar_init(s_bar(t), 1);
             mbar_init(p_bar(t), 4);
+            mbar_init(pb_bar(t), 4);
             mbar_init(o_bar(t), 1);
             mbar_init(free_bar(t), 4);
             mbar_init(ofull_bar(t), 4);
@@ -287,13 +304,18 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             };
             auto issue_pv = [&](int t, int it_) {
                 const uint32_t sV = base + (it_ & 1) * STAGE_BYTES_TC + Q_BYTES + KV_BYTES;
-                mbar_wait(p_bar(t), it_ & 1);                       // softmax has written P_t into TMEM
-                tc_fence_after();
                 const uint64_t dv = make_sw128_mn_desc(sV, KV_BYTES);
-                const uint32_t to = tmem_base + t * TILE_COLS + O_COL, tp = tmem_base + t * TILE_COLS + P_COL;
+                const uint32_t to = tmem_base + t * TILE_COLS + O_COL, tp = tmem_base + t * TILE_COLS + P_COL, tpb = tmem_base + t * TILE_COLS + PB_COL;
+                mbar_wait(p_bar(t), it_ & 1);                       // softmax has written P_t of keys 0..127 into TMEM
+                tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < static_cast<int>(KV_ROWS) / 16; ++k)          // 16 keys = 2 KB of V = 128 units of the descriptor's address field
+                for (int k = 0; k < kKeysA / 16; ++k)                             // 16 keys = 2 KB of V = 128 units of the descriptor's address field
                     umma_bf16_ts(to, tp + k * 8, dv + 128 * k, idesc_o, static_cast<uint32_t>(k != 0));
+                mbar_wait(pb_bar(t), it_ & 1);                      // ... and of the remaining keys
+                tc_fence_after();
+#pragma unroll
+                for (int k = kKeysA / 16; k < static_cast<int>(KV_ROWS) / 16; ++k)
+                    umma_bf16_ts(to, tpb + (k - kKeysA / 16) * 8, dv + 128 * k, idesc_o, 1u);
                 umma_commit(o_bar(t));
             };
             int it = 0;
@@ -408,7 +430,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                         }
                     }
                     tmem_ld_wait_dep(rb);
-                    tmem_st16(trow + P_COL + c * 16, pk);
+                    tmem_st16(trow + (c < 4 ? P_COL + c * 16 : PB_COL + (c - 4) * 16), pk);
                     if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
                     if (kFull192 || (c + 2) * 32 <= d.Lk) {
                         softmax_max32(rb, run);
@@ -426,7 +448,13 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                         }
                     }
                     tmem_ld_wait_dep(ra);
-                    tmem_st16(trow + P_COL + (c + 1) * 16, pk);
+                    tmem_st16(trow + (c < 4 ? P_COL + (c + 1) * 16 : PB_COL + (c - 3) * 16), pk);
+                    if (c == 2) {            // P of keys 0..127 is complete: the tensor core may start on O while the rest is exponentiated
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(p_bar(t));
+                    }
                     // the chunk now in `ra` (32 columns, or the 16-column tail after the last round) joins the running maximum
                     if (c + 2 < 6) {
                         if (kFull192 || (c + 3) * 32 <= d.Lk) softmax_max32(ra, run);
@@ -448,7 +476,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                         sum += p0 + p1;
                         pt[j >> 1] = pack_bf16x2(p0, p1);
                     }
-                    tmem_st8(trow + P_COL + 96, pt);
+                    tmem_st8(trow + PB_COL + 32, pt);
                 }
                 redo = !(fmaf(run, sl2, -mxs) <= kMaxAboveRef);      // also true for a NaN score row: recomputed the slow way, still NaN
                 tmem_st_wait();
@@ -461,7 +489,10 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 if (lane == 0) flags[static_cast<int64_t>(prob) * 8 + warp] = redo_rows;
             }
             if ((warp & 3) == 0) SFB_TS(8 + 8 * t);
-            if (lane == 0) mbar_arrive(p_bar(t));
+            if (lane == 0) {
+                if (!rows_live) mbar_arrive(p_bar(t));              // an all-padding warp skipped the pass (and its mid-pass arrival)
+                mbar_arrive(pb_bar(t));
+            }
             // ---- while the tensor core forms O_t: next problem's indices, and the staging tile must be free again
             pidx.advance();
             if (tma_out && it > 0) mbar_wait(ofree_bar(t), (it - 1) & 1);    // the previous problem's store has finished reading the staging tile
