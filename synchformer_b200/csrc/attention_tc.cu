@@ -478,7 +478,10 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     }
                     tmem_st8(trow + PB_COL + 32, pt);
                 }
-                redo = !(fmaf(run, sl2, -mxs) <= kMaxAboveRef);      // also true for a NaN score row: recomputed the slow way, still NaN
+                {   // rows with infinite / NaN scores are left alone: they come out non-finite either way, as in the reference
+                    const float over = fmaf(run, sl2, -mxs);
+                    redo = over > kMaxAboveRef && over < INFINITY;
+                }
                 tmem_st_wait();
                 inv = 1.0f / sum;
                 mxs_keep = mxs, sum_keep = sum;
