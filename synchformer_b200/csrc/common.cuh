@@ -42,6 +42,7 @@ struct PerDeviceOnce {
     void reset_current();            // setup failed: try again on the next call
 };
 int encode_tmap_bf16_2d(void *map, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
+int encode_tmap_f32_2d(void *map, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols, bool swizzle128);
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 

@@ -51,6 +51,8 @@ constexpr int UMMA_K = 16;
 constexpr int kAccStages = 2;
 constexpr int kEpiWarps = 16;  // 4 per TMEM lane quarter: the epilogue is latency-bound per warp, so it wants warps, not ILP
 constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kEpiWarpsTma = 8;                                  // EPI_F32_TMA: 2 per lane quarter, 8 KB of staging each (no per-thread global access)
+constexpr int kThreadsTma = 64 + kEpiWarpsTma * 32;
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;               // 16 KB: this CTA's 128 rows of A
 constexpr uint32_t EPI_WARP_BYTES = 4096;                        // 32 rows x 128 B transpose buffer per epilogue warp
 constexpr uint32_t TMEM_COLS = 512;
@@ -88,6 +90,7 @@ struct EpiParams {
     __nv_bfloat16 *emit_bf16; // EMIT_LN: bf16 copy of the output rows, row stride ld_emit
     int64_t ld_emit;
     int tma_store;            // bf16 output tiles leave through cp.async.bulk.tensor (UTMASTG) instead of per-thread st.global
+    int prefetch_res;         // EPI_F32_TMA: every epilogue warp pulls the residual boxes of its NEXT tile into L2 while it works on this one
 };
 
 // ------------------------------------------------------------------------------------------ cluster helpers
@@ -139,18 +142,25 @@ constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the bit that distingu
 //   EPI_F32      fp32 output (bias, optional GELU / residual)      EPI_F32_LN   the same + bf16 copy and row statistics (SFB_GEMM_EMIT_LN)
 // (A third cluster shape - two pairs sharing every W tile through TMA multicast, 48 instead of 64 bytes of L2 reads per MMA clock - was
 // built and measured 3-8 % slower in round 1: multicast removes L2 reads, not bytes entering the SM, and 4-CTA clusters strand SMs.)
-enum { EPI_BF16 = 0, EPI_BF16_LN = 1, EPI_F32 = 2, EPI_F32_LN = 3 };
+//   EPI_F32_TMA  fp32 output (bias, optional GELU / residual, optional EMIT_LN) with NO per-thread global access: 8 epilogue warps, each
+//                with a 4 KB fp32 tile (32 rows x 32 columns, 128B-swizzled = the TMA box layout) and a 4 KB bf16 tile.  The residual box
+//                arrives by TMA load (its lines were pulled into L2 by the producer a tile earlier), every thread adds its accumulator
+//                row segment IN PLACE (row-per-thread mapping: the LayerNorm statistics of EMIT_LN are plain per-thread sums, no
+//                shuffles), and the tile leaves by TMA store; the bf16 copy of EMIT_LN leaves the same way.
+enum { EPI_BF16 = 0, EPI_BF16_LN = 1, EPI_F32 = 2, EPI_F32_LN = 3, EPI_F32_TMA = 4 };
 
 template <int CG, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)   // 18 warps are allocated as 20 (granularity 4): 96 registers per thread
+__global__ void __launch_bounds__(EPI == EPI_F32_TMA ? kThreadsTma : kThreads, 1)   // 18 warps are allocated as 20 (granularity 4): 96 registers per thread
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                         const __grid_constant__ CUtensorMap tmap_out, const EpiParams p) {
+                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                         const __grid_constant__ CUtensorMap tmap_emit, const EpiParams p) {
     using C = Cfg<CG>;
     constexpr int CL = CG;
     constexpr int kStages = C::kStages;
     constexpr uint32_t STAGE_BYTES = C::STAGE_BYTES;
+    constexpr int kEpiW = EPI == EPI_F32_TMA ? kEpiWarpsTma : kEpiWarps;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kAccStages];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kAccStages + kEpiWarpsTma];    // ... + one "residual box landed" barrier per TMA-epilogue warp
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5;
@@ -168,6 +178,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
         if (p.tma_store) tma_prefetch_desc(&tmap_out);
+        if (EPI == EPI_F32_TMA) {
+            tma_prefetch_desc(&tmap_out), tma_prefetch_desc(&tmap_res), tma_prefetch_desc(&tmap_emit);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -176,7 +189,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         for (int a = 0; a < kAccStages; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), kEpiWarps * CG);   // epilogue warps of every CTA of the pair arrive on the leader's barrier
+            mbar_init(tempty_bar(a), kEpiW * CG);   // epilogue warps of every CTA of the pair arrive on the leader's barrier
+        }
+        if (EPI == EPI_F32_TMA) {
+            for (int w = 0; w < kEpiWarpsTma; ++w) mbar_init(bar_base + 8u * (2 * kMaxStages + 2 * kAccStages + w), 1);
         }
         fence_barrier_init();
     }
@@ -269,6 +285,146 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             }
         }
+    } else if (EPI == EPI_F32_TMA) {
+        // ================================ epilogue, fp32 tiles through TMA both ways ===
+        // warp (q, half) owns accumulator rows [32q, 32q+32) x columns [128 half, 128 half + 128): four 32-column chunks per tile.
+        const int q = warp & 3;                      // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;
+        const bool gelu = (p.flags & SFB_GEMM_GELU) != 0;
+        const bool has_res = (p.flags & SFB_GEMM_RESIDUAL) != 0 && !(p.flags & DBG_NORES);
+        const bool emit = (p.flags & SFB_GEMM_EMIT_LN) != 0;
+        const bool do_store = !(p.flags & DBG_NOSTORE);
+        uint8_t *xt = smem_raw + (tiles_base - smem_u32(smem_raw)) + kStages * STAGE_BYTES + (warp - 2) * 8192;     // fp32 tile, 32 rows x 128 B
+        uint8_t *bt = xt + 4096;                                                                                  // bf16 tile, 32 rows x 128 B (64 columns)
+        const uint32_t xt_s = smem_u32(xt), bt_s = smem_u32(bt);
+        uint8_t *xrow = xt + lane * 128, *brow = bt + lane * 128;
+        const int sw = lane & 7;                                       // 16-byte chunk k of row r lives at chunk k ^ (r & 7): SWIZZLE_128B
+        const uint32_t rbar = bar_base + 8u * (2 * kMaxStages + 2 * kAccStages + (warp - 2));
+        uint32_t rphase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(tempty_bar(0), 0u) : tempty_bar(0);
+        auto tile_origin = [&](int tile, int &m0w, int &n0w) {
+            m0w = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CL) + crank * BLOCK_M + q * 32;
+            n0w = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + half * 128;
+        };
+        auto request_residual = [&](int m0w, int col) {               // lane 0: the box lands in xt and completes rbar
+            mbar_arrive_expect_tx(rbar, 4096u);
+            tma_load_2d(xt_s, &tmap_res, rbar, col, m0w);
+        };
+        // one tile ahead: the boxes are pulled into L2 while the warp works on the previous tile (a single 4 KB box in flight per warp would
+        // leave every chunk waiting ~2 us for HBM; earlier than one tile ahead and the lines are evicted again by the streaming writes)
+        auto prefetch_boxes = [&](int m0w, int n0w, int c_first) {
+            for (int c = c_first; c < 4; ++c)
+                if (n0w + c * 32 < p.N) tma_prefetch_l2_2d(&tmap_res, n0w + c * 32, m0w);
+        };
+        {
+            int m0w, n0w;
+            tile_origin(first_tile, m0w, n0w);
+            if (first_tile < num_tiles && has_res && lane == 0 && m0w < p.M && n0w < p.N) {
+                request_residual(m0w, n0w);
+                if (p.prefetch_res) prefetch_boxes(m0w, n0w, 1);
+            }
+        }
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            int m0w, n0w, m0n = 0, n0n = 0;
+            tile_origin(tile, m0w, n0w);
+            const bool next_tile = tile + tile_step < num_tiles;
+            if (next_tile) tile_origin(tile + tile_step, m0n, n0n);
+            const bool live = m0w < p.M;                               // warp-uniform
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + half * 128);
+            if (has_res && p.prefetch_res && lane == 0 && next_tile && m0n < p.M) prefetch_boxes(m0n, n0n, 0);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            uint32_t r[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(tbase + c * 32, r[c]);
+            tmem_ld_wait();
+            tc_fence_before();                                         // the accumulator goes back to the MMA issuer before any of the epilogue math
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+            }
+            float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};              // EMIT_LN: (sum, sum of squares) of this thread's row per 64-column group
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col = n0w + c * 32;
+                if (live && col < p.N) {                               // warp-uniform
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c][j]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col + j < p.N) {
+                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col + j));
+                                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+                            }
+                        }
+                    }
+                    if (gelu) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
+                    }
+                    if (has_res) {
+                        mbar_wait(rbar, rphase);
+                        rphase ^= 1u;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 rv = *reinterpret_cast<const float4 *>(xrow + ((k ^ sw) << 4));
+                            v[4 * k] += rv.x, v[4 * k + 1] += rv.y, v[4 * k + 2] += rv.z, v[4 * k + 3] += rv.w;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        *reinterpret_cast<float4 *>(xrow + ((k ^ sw) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    if (emit) {
+                        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) a1 += v[j], a2 = fmaf(v[j], v[j], a2);
+                        s1[c >> 1] += a1, s2[c >> 1] += a2;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            *reinterpret_cast<uint4 *>(brow + ((((c & 1) * 4 + k) ^ sw) << 4)) =
+                                make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                           pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                    }
+                    fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA unit
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (do_store) {
+                            tma_store_2d(&tmap_out, xt_s, col, m0w);   // rows >= M / columns >= N are clipped by the unit
+                            if (emit && (c & 1)) tma_store_2d(&tmap_emit, bt_s, n0w + (c >> 1) * 64, m0w);
+                            tma_store_commit();
+                            tma_store_wait_read();                     // the tiles may be overwritten
+                        }
+                        // the next box this warp will need: the next chunk of this tile, else the first chunk of the next tile
+                        if (has_res) {
+                            if (c < 3 && col + 32 < p.N) request_residual(m0w, col + 32);
+                            else if (next_tile && m0n < p.M && n0n < p.N) request_residual(m0n, n0n);
+                        }
+                    }
+                    __syncwarp();
+                } else if (c == 0 && has_res && lane == 0 && next_tile && m0n < p.M && n0n < p.N) {
+                    request_residual(m0n, n0n);                        // this warp had nothing to do in this tile; keep the chain going
+                }
+            }
+            if (emit && live) {
+                const int64_t grow = m0w + lane;
+                if (grow < p.M && do_store) {
+#pragma unroll
+                    for (int g2 = 0; g2 < 2; ++g2) {
+                        const int gcol = n0w + g2 * 64;
+                        if (gcol < p.N) *reinterpret_cast<float2 *>(p.emit_stats + (grow * (p.N >> 6) + (gcol >> 6)) * 2) = make_float2(s1[g2], s2[g2]);
+                    }
+                }
+            }
+            if (++acc == kAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+        if (lane == 0) tma_store_wait_all();                           // shared memory must outlive the bulk stores that read it
     } else {
         // ================================ epilogue ====================================
         // TMEM -> registers (one accumulator row per thread) -> bias / GELU -> per-warp 4 KB shared-memory transpose buffer
@@ -644,7 +800,13 @@ extern "C" int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const
     SFB_CHECK_ARG(impl == 0 || impl == 2 || impl == 3, "sfb_gemm_bf16: unknown impl %d (0 auto, 1 CUDA-core check, 2 single-CTA, 3 CTA-pair)", impl);
     // CTA pairs (256-row tiles) unless the problem has at most one 128-row block
     const int cg = impl == 2 ? 1 : impl == 3 ? 2 : (M > BLOCK_M ? 2 : 1);
-    const int epi = (flags & SFB_GEMM_OUT_F32) ? ((flags & SFB_GEMM_EMIT_LN) ? EPI_F32_LN : EPI_F32) : ((flags & SFB_GEMM_LN_FOLD) ? EPI_BF16_LN : EPI_BF16);
+    int epi = (flags & SFB_GEMM_OUT_F32) ? ((flags & SFB_GEMM_EMIT_LN) ? EPI_F32_LN : EPI_F32) : ((flags & SFB_GEMM_LN_FOLD) ? EPI_BF16_LN : EPI_BF16);
+    // fp32 outputs go through the TMA epilogue whenever their rows form regular 2D tensors (SFB_GEMM_F32_TMA=0: per-thread epilogue, A/B aid);
+    // a broadcast residual row (ldr == 0) and unaligned EMIT_LN copies stay on the per-thread epilogue
+    const int f32_tma_env = getenv("SFB_GEMM_F32_TMA") ? atoi(getenv("SFB_GEMM_F32_TMA")) : 1;             // read per call: tools/gemm_ab.py flips it
+    if ((flags & SFB_GEMM_OUT_F32) && f32_tma_env && ldo % 4 == 0 && (!(flags & SFB_GEMM_RESIDUAL) || ldr >= N) &&
+        (!(flags & SFB_GEMM_EMIT_LN) || ((reinterpret_cast<uintptr_t>(emit_bf16) & 15) == 0 && ld_emit % 8 == 0)))
+        epi = EPI_F32_TMA;
 
     CUtensorMap tmap_a, tmap_w;
     int rc = make_tmap(&tmap_a, A, M, K, lda, BLOCK_M);
@@ -653,26 +815,36 @@ extern "C" int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const
     if (rc != SFB_OK) return rc;
     // bf16 outputs leave through TMA stores: one 32-row x 64-column box per epilogue warp (SFB_GEMM_TMA_STORE=0: per-thread st.global, A/B aid)
     static const int tma_store_env = getenv("SFB_GEMM_TMA_STORE") ? atoi(getenv("SFB_GEMM_TMA_STORE")) : 1;
-    CUtensorMap tmap_out = tmap_a;
-    p.tma_store = 0;
+    CUtensorMap tmap_out = tmap_a, tmap_res = tmap_a, tmap_emit = tmap_a;
+    p.tma_store = 0, p.prefetch_res = 0;
     if (tma_store_env && !(flags & SFB_GEMM_OUT_F32)) {
         rc = encode_tmap_bf16_2d(&tmap_out, out, M, N, ldo, 32, 64);
         if (rc != SFB_OK) return rc;
         p.tma_store = 1;
+    }
+    if (epi == EPI_F32_TMA) {
+        rc = encode_tmap_f32_2d(&tmap_out, out, M, N, ldo, 32, 32, true);
+        if (rc == SFB_OK && (flags & SFB_GEMM_RESIDUAL)) {
+            const int pref_env = getenv("SFB_GEMM_RES_PREFETCH") ? atoi(getenv("SFB_GEMM_RES_PREFETCH")) : 0;    // measured: the prefetch costs 5 - 7 % (tools/gemm_ab.py)
+            rc = encode_tmap_f32_2d(&tmap_res, residual, M, N, ldr, 32, 32, true);
+            p.prefetch_res = pref_env;
+        }
+        if (rc == SFB_OK && (flags & SFB_GEMM_EMIT_LN)) rc = encode_tmap_bf16_2d(&tmap_emit, emit_bf16, M, N, ld_emit, 32, 64);
+        if (rc != SFB_OK) return rc;
     }
 
     static PerDeviceOnce attr_once;
     if (attr_once.first()) {
 #define SFB_GEMM_ATTR(CGV, EPIV) \
     SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<CGV, EPIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CGV>::SMEM_BYTES))
-        SFB_GEMM_ATTR(1, EPI_BF16); SFB_GEMM_ATTR(1, EPI_BF16_LN); SFB_GEMM_ATTR(1, EPI_F32); SFB_GEMM_ATTR(1, EPI_F32_LN);
-        SFB_GEMM_ATTR(2, EPI_BF16); SFB_GEMM_ATTR(2, EPI_BF16_LN); SFB_GEMM_ATTR(2, EPI_F32); SFB_GEMM_ATTR(2, EPI_F32_LN);
+        SFB_GEMM_ATTR(1, EPI_BF16); SFB_GEMM_ATTR(1, EPI_BF16_LN); SFB_GEMM_ATTR(1, EPI_F32); SFB_GEMM_ATTR(1, EPI_F32_LN); SFB_GEMM_ATTR(1, EPI_F32_TMA);
+        SFB_GEMM_ATTR(2, EPI_BF16); SFB_GEMM_ATTR(2, EPI_BF16_LN); SFB_GEMM_ATTR(2, EPI_F32); SFB_GEMM_ATTR(2, EPI_F32_LN); SFB_GEMM_ATTR(2, EPI_F32_TMA);
 #undef SFB_GEMM_ATTR
     }
     p.num_m_blocks = (M + cg * BLOCK_M - 1) / (cg * BLOCK_M);           // 128-row (single CTA) or 256-row (pair) tiles
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(epi == EPI_F32_TMA ? kThreadsTma : kThreads);
     cfg.dynamicSmemBytes = cg == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -682,12 +854,14 @@ extern "C" int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const
     const int max_clusters = num_sms() / cg;
     const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
     cfg.gridDim = dim3(cg * clusters);
-#define SFB_GEMM_LAUNCH(CGV, EPIV) SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<CGV, EPIV>, tmap_a, tmap_w, tmap_out, p))
+#define SFB_GEMM_LAUNCH(CGV, EPIV) \
+    SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<CGV, EPIV>, tmap_a, tmap_w, tmap_out, tmap_res, tmap_emit, p))
     if (cg == 2) {
         switch (epi) {
             case EPI_BF16: SFB_GEMM_LAUNCH(2, EPI_BF16); break;
             case EPI_BF16_LN: SFB_GEMM_LAUNCH(2, EPI_BF16_LN); break;
             case EPI_F32: SFB_GEMM_LAUNCH(2, EPI_F32); break;
+            case EPI_F32_TMA: SFB_GEMM_LAUNCH(2, EPI_F32_TMA); break;
             default: SFB_GEMM_LAUNCH(2, EPI_F32_LN); break;
         }
     } else {
@@ -695,6 +869,7 @@ extern "C" int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const
             case EPI_BF16: SFB_GEMM_LAUNCH(1, EPI_BF16); break;
             case EPI_BF16_LN: SFB_GEMM_LAUNCH(1, EPI_BF16_LN); break;
             case EPI_F32: SFB_GEMM_LAUNCH(1, EPI_F32); break;
+            case EPI_F32_TMA: SFB_GEMM_LAUNCH(1, EPI_F32_TMA); break;
             default: SFB_GEMM_LAUNCH(1, EPI_F32_LN); break;
         }
     }

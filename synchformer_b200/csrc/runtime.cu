@@ -83,6 +83,29 @@ int encode_tmap_bf16_2d(void *map, const void *base, int64_t rows, int64_t cols,
     return SFB_OK;
 }
 
+// The same for a 2D fp32 row-major matrix: box (box_rows x box_cols); `swizzle128` = 128B swizzle (box_cols * 4 bytes must be 128, used for
+// shared-memory tiles) or none (boxes that are only prefetched into L2: up to 256 columns).
+int encode_tmap_f32_2d(void *map, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols, bool swizzle128) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return SFB_E_CUDA;
+    }
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap *>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d (rows %lld cols %lld ld %lld box %d x %d)", static_cast<int>(r),
+                  static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld), box_rows, box_cols);
+        return SFB_E_CUDA;
+    }
+    return SFB_OK;
+}
+
 }  // namespace sfb
 
 extern "C" int sfb_abi_version(void) { return 1; }
