@@ -90,7 +90,6 @@ struct EpiParams {
     __nv_bfloat16 *emit_bf16; // EMIT_LN: bf16 copy of the output rows, row stride ld_emit
     int64_t ld_emit;
     int tma_store;            // bf16 output tiles leave through cp.async.bulk.tensor (UTMASTG) instead of per-thread st.global
-    int prefetch_res;         // EPI_F32_TMA: every epilogue warp pulls the residual boxes of its NEXT tile into L2 while it works on this one
 };
 
 // ------------------------------------------------------------------------------------------ cluster helpers
@@ -160,7 +159,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     constexpr uint32_t STAGE_BYTES = C::STAGE_BYTES;
     constexpr int kEpiW = EPI == EPI_F32_TMA ? kEpiWarpsTma : kEpiWarps;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kAccStages + kEpiWarpsTma];    // ... + one "residual box landed" barrier per TMA-epilogue warp
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kAccStages + 2 * kEpiWarpsTma];    // ... + two "residual box landed" barriers per TMA-epilogue warp
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5;
@@ -192,7 +191,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             mbar_init(tempty_bar(a), kEpiW * CG);   // epilogue warps of every CTA of the pair arrive on the leader's barrier
         }
         if (EPI == EPI_F32_TMA) {
-            for (int w = 0; w < kEpiWarpsTma; ++w) mbar_init(bar_base + 8u * (2 * kMaxStages + 2 * kAccStages + w), 1);
+            for (int w = 0; w < 2 * kEpiWarpsTma; ++w) mbar_init(bar_base + 8u * (2 * kMaxStages + 2 * kAccStages + w), 1);
         }
         fence_barrier_init();
     }
@@ -294,46 +293,50 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const bool has_res = (p.flags & SFB_GEMM_RESIDUAL) != 0 && !(p.flags & DBG_NORES);
         const bool emit = (p.flags & SFB_GEMM_EMIT_LN) != 0;
         const bool do_store = !(p.flags & DBG_NOSTORE);
-        uint8_t *xt = smem_raw + (tiles_base - smem_u32(smem_raw)) + kStages * STAGE_BYTES + (warp - 2) * 8192;     // fp32 tile, 32 rows x 128 B
-        uint8_t *bt = xt + 4096;                                                                                  // bf16 tile, 32 rows x 128 B (64 columns)
-        const uint32_t xt_s = smem_u32(xt), bt_s = smem_u32(bt);
-        uint8_t *xrow = xt + lane * 128, *brow = bt + lane * 128;
+        // per warp: two 4 KB tiles (32 rows x 128 B, 128B-swizzled = the TMA box layout).  Without EMIT_LN both hold fp32 chunks alternately
+        // (the residual box of chunk g+2 is requested as soon as the store of chunk g has left its tile: two boxes in flight per warp);
+        // with EMIT_LN the second tile collects the bf16 copy of two chunks (64 columns) and the fp32 chunks use the first tile only.
+        uint8_t *xt = smem_raw + (tiles_base - smem_u32(smem_raw)) + kStages * STAGE_BYTES + (warp - 2) * 8192;
+        const uint32_t xt_s = smem_u32(xt), bt_s = xt_s + 4096;
+        uint8_t *brow = xt + 4096 + lane * 128;
         const int sw = lane & 7;                                       // 16-byte chunk k of row r lives at chunk k ^ (r & 7): SWIZZLE_128B
-        const uint32_t rbar = bar_base + 8u * (2 * kMaxStages + 2 * kAccStages + (warp - 2));
-        uint32_t rphase = 0;
-        int acc = 0;
+        const uint32_t rbar0 = bar_base + 8u * (2 * kMaxStages + 2 * kAccStages + 2 * (warp - 2));
+        const int depth = emit ? 1 : 2;                                // residual boxes in flight
+        uint32_t rphase = 0;                                           // bit b: parity of tile b's barrier
+        int acc = 0, g = 0;                                            // g: valid chunks processed so far (its parity selects the tile)
         uint32_t acc_phase = 0;
         const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(tempty_bar(0), 0u) : tempty_bar(0);
         auto tile_origin = [&](int tile, int &m0w, int &n0w) {
             m0w = (p.m_fastest ? tile % p.num_m_blocks : tile / p.num_n_blocks) * (BLOCK_M * CL) + crank * BLOCK_M + q * 32;
             n0w = (p.m_fastest ? tile / p.num_m_blocks : tile % p.num_n_blocks) * BLOCK_N + half * 128;
         };
-        auto request_residual = [&](int m0w, int col) {               // lane 0: the box lands in xt and completes rbar
-            mbar_arrive_expect_tx(rbar, 4096u);
-            tma_load_2d(xt_s, &tmap_res, rbar, col, m0w);
-        };
-        // one tile ahead: the boxes are pulled into L2 while the warp works on the previous tile (a single 4 KB box in flight per warp would
-        // leave every chunk waiting ~2 us for HBM; earlier than one tile ahead and the lines are evicted again by the streaming writes)
-        auto prefetch_boxes = [&](int m0w, int n0w, int c_first) {
-            for (int c = c_first; c < 4; ++c)
-                if (n0w + c * 32 < p.N) tma_prefetch_l2_2d(&tmap_res, n0w + c * 32, m0w);
-        };
-        {
-            int m0w, n0w;
-            tile_origin(first_tile, m0w, n0w);
-            if (first_tile < num_tiles && has_res && lane == 0 && m0w < p.M && n0w < p.N) {
-                request_residual(m0w, n0w);
-                if (p.prefetch_res) prefetch_boxes(m0w, n0w, 1);
+        // request cursor: walks the chunks this warp will process (tiles in order, chunks 0..3, skipping rows >= M / columns >= N), `depth` ahead
+        int q_tile = first_tile, q_c = -1, q_m = 0, q_col = 0, q_n = 0;      // q_n: boxes requested so far
+        bool q_valid = has_res;
+        auto request_next = [&]() {                                   // warp-uniform bookkeeping, lane 0 issues
+            while (q_valid) {
+                if (q_c < 3) ++q_c; else q_tile += tile_step, q_c = 0;
+                if (q_tile >= num_tiles) { q_valid = false; break; }
+                int m, n;
+                tile_origin(q_tile, m, n);
+                if (m < p.M && n + q_c * 32 < p.N) { q_m = m, q_col = n + q_c * 32; break; }
+                q_c = 3;                                              // nothing (more) to do in this tile
             }
-        }
+            if (q_valid) {
+                const int bsel = emit ? 0 : (q_n & 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(rbar0 + 8u * bsel, 4096u);
+                    tma_load_2d(xt_s + 4096u * bsel, &tmap_res, rbar0 + 8u * bsel, q_col, q_m);
+                }
+                ++q_n;
+            }
+        };
+        for (int i = 0; i < depth; ++i) request_next();
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-            int m0w, n0w, m0n = 0, n0n = 0;
+            int m0w, n0w;
             tile_origin(tile, m0w, n0w);
-            const bool next_tile = tile + tile_step < num_tiles;
-            if (next_tile) tile_origin(tile + tile_step, m0n, n0n);
             const bool live = m0w < p.M;                               // warp-uniform
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + half * 128);
-            if (has_res && p.prefetch_res && lane == 0 && next_tile && m0n < p.M) prefetch_boxes(m0n, n0n, 0);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             uint32_t r[4][32];
@@ -350,6 +353,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             for (int c = 0; c < 4; ++c) {
                 const int col = n0w + c * 32;
                 if (live && col < p.N) {                               // warp-uniform
+                    const int bsel = emit ? 0 : (g & 1);
+                    uint8_t *xrow = xt + 4096 * bsel + lane * 128;
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c][j]);
@@ -367,8 +372,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int j = 0; j < 32; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
                     }
                     if (has_res) {
-                        mbar_wait(rbar, rphase);
-                        rphase ^= 1u;
+                        mbar_wait(rbar0 + 8u * bsel, (rphase >> bsel) & 1u);
+                        rphase ^= 1u << bsel;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float4 rv = *reinterpret_cast<const float4 *>(xrow + ((k ^ sw) << 4));
@@ -391,22 +396,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                     fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA unit
                     __syncwarp();
-                    if (lane == 0) {
-                        if (do_store) {
-                            tma_store_2d(&tmap_out, xt_s, col, m0w);   // rows >= M / columns >= N are clipped by the unit
-                            if (emit && (c & 1)) tma_store_2d(&tmap_emit, bt_s, n0w + (c >> 1) * 64, m0w);
-                            tma_store_commit();
-                            tma_store_wait_read();                     // the tiles may be overwritten
-                        }
-                        // the next box this warp will need: the next chunk of this tile, else the first chunk of the next tile
-                        if (has_res) {
-                            if (c < 3 && col + 32 < p.N) request_residual(m0w, col + 32);
-                            else if (next_tile && m0n < p.M && n0n < p.N) request_residual(m0n, n0n);
-                        }
+                    if (lane == 0 && do_store) {
+                        tma_store_2d(&tmap_out, xt_s + 4096u * bsel, col, m0w);          // rows >= M / columns >= N are clipped by the unit
+                        if (emit && (c & 1)) tma_store_2d(&tmap_emit, bt_s, n0w + (c >> 1) * 64, m0w);
+                        tma_store_commit();
+                        tma_store_wait_read();                         // this tile may be overwritten: by the next residual box, or by chunk g + depth
                     }
                     __syncwarp();
-                } else if (c == 0 && has_res && lane == 0 && next_tile && m0n < p.M && n0n < p.N) {
-                    request_residual(m0n, n0n);                        // this warp had nothing to do in this tile; keep the chain going
+                    request_next();                                    // the box of chunk g + depth goes into the tile that has just been stored
+                    ++g;
                 }
             }
             if (emit && live) {
@@ -816,7 +814,7 @@ extern "C" int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const
     // bf16 outputs leave through TMA stores: one 32-row x 64-column box per epilogue warp (SFB_GEMM_TMA_STORE=0: per-thread st.global, A/B aid)
     static const int tma_store_env = getenv("SFB_GEMM_TMA_STORE") ? atoi(getenv("SFB_GEMM_TMA_STORE")) : 1;
     CUtensorMap tmap_out = tmap_a, tmap_res = tmap_a, tmap_emit = tmap_a;
-    p.tma_store = 0, p.prefetch_res = 0;
+    p.tma_store = 0;
     if (tma_store_env && !(flags & SFB_GEMM_OUT_F32)) {
         rc = encode_tmap_bf16_2d(&tmap_out, out, M, N, ldo, 32, 64);
         if (rc != SFB_OK) return rc;
@@ -825,9 +823,7 @@ extern "C" int sfb_gemm_bf16_ln(const void *A, int64_t lda, const void *W, const
     if (epi == EPI_F32_TMA) {
         rc = encode_tmap_f32_2d(&tmap_out, out, M, N, ldo, 32, 32, true);
         if (rc == SFB_OK && (flags & SFB_GEMM_RESIDUAL)) {
-            const int pref_env = getenv("SFB_GEMM_RES_PREFETCH") ? atoi(getenv("SFB_GEMM_RES_PREFETCH")) : 0;    // measured: the prefetch costs 5 - 7 % (tools/gemm_ab.py)
             rc = encode_tmap_f32_2d(&tmap_res, residual, M, N, ldr, 32, 32, true);
-            p.prefetch_res = pref_env;
         }
         if (rc == SFB_OK && (flags & SFB_GEMM_EMIT_LN)) rc = encode_tmap_bf16_2d(&tmap_emit, emit_bf16, M, N, ld_emit, 32, 64);
         if (rc != SFB_OK) return rc;

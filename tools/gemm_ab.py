@@ -1,5 +1,5 @@
 """Same-process, interleaved A/B of the fp32-output GEMM epilogues at the benchmark shapes (512 segments): per-thread epilogue
-(SFB_GEMM_F32_TMA=0) vs TMA epilogue without / with the L2 prefetch of the next tile's residual boxes.  The switches are read per call,
+(SFB_GEMM_F32_TMA=0) vs the TMA epilogue.  The switch is read per call,
 so the variants alternate round-robin inside one process (same clocks, same thermal state); medians over the rounds are printed."""
 import os
 import statistics
@@ -11,8 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from synchformer_b200 import ops  # noqa: E402
 
 D = 768
-VARIANTS = {'per-thread': {'SFB_GEMM_F32_TMA': '0'}, 'tma': {'SFB_GEMM_F32_TMA': '1', 'SFB_GEMM_RES_PREFETCH': '0'},
-            'tma+l2prefetch': {'SFB_GEMM_F32_TMA': '1', 'SFB_GEMM_RES_PREFETCH': '1'}}
+VARIANTS = {'per-thread': {'SFB_GEMM_F32_TMA': '0'}, 'tma': {'SFB_GEMM_F32_TMA': '1'}}
 
 
 def timeit(fn, iters=40):
