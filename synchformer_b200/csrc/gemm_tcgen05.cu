@@ -15,8 +15,11 @@
 //   warp 1      MMA issuer     one thread issues 4 x tcgen05.mma.kind::f16 (M 128*CG, N256, K16) per stage,
 //                              accumulating in TMEM; tcgen05.commit releases the stage ("empty") and, after the
 //                              last k-block, publishes the accumulator ("tmem_full")
-//   warps 2-17  epilogue       tcgen05.ld 32x32b.x32 (TMEM -> registers), bias / GELU, transpose through a swizzled per-warp
-//                              shared-memory buffer, then row-contiguous residual loads and 16-byte stores;
+//   warps 2-17  epilogue       tcgen05.ld 32x32b.x32 (TMEM -> registers), bias / GELU, a swizzled per-warp shared-memory tile in the
+//                              TMA box layout, TMA store (bf16 outputs).  fp32 outputs (EPI_F32_TMA, 8 epilogue warps): the fp32
+//                              residual box comes in by TMA load, the accumulator is added in place, the tile leaves by TMA store -
+//                              no per-thread global access (the older per-thread fp32 epilogues remain for broadcast residual rows
+//                              and as the A/B baseline);
 //                              the 512 TMEM columns hold TWO 128x256 fp32 accumulators so the epilogue of tile i
 //                              overlaps the main loop of tile i+1
 // LayerNorm fusion (the 36 LayerNorm passes of the Motionformer blocks disappear; vit_helper.py:366-375):
