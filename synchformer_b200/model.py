@@ -205,9 +205,11 @@ class MotionFormer(_KernelModule):
         self.embed_dim, self.num_heads = D, 12
         self.max_segments_per_pass = 512
         # LayerNorm fused into the GEMMs on either side of it (csrc/gemm_tcgen05.cu: EMIT_LN / LN_FOLD) instead of 36 LayerNorm launches per
-        # pass.  Opt-in (SFB_LN_FUSED=1): measured on the B200 (profiles/r2_ln_fusion_ab.txt) the fused schedule removes 20 ms of LayerNorm
-        # passes per 64-clip step but adds 34 ms to the GEMM epilogues, which are the bottleneck of those kernels already.
-        self.fuse_layernorm = os.environ.get('SFB_LN_FUSED', '0') == '1'
+        # pass.  Opt-in (SFB_LN_FUSED=1 / 2): measured on the B200 the fused schedules remove 13 - 21 ms of LayerNorm passes per 64-clip step and
+        # add as much to the GEMM epilogues (profiles/r2_ab_f32_tma_epilogue.txt, r2_ab_ln_fusion_modes.txt).
+        # 2 = only the two norms in front of the qkv GEMMs (norm3, norm1) are fused; norm2 keeps its LayerNorm launch, because the folded
+        # epilogue costs 0.16 ms on a qkv GEMM but 0.66 ms on fc1, whose epilogue already carries the GELU (tools/gemm_ab.py)
+        self.fuse_layernorm = int(os.environ.get('SFB_LN_FUSED', '0'))
         schema = {k[len('vfeat_extractor.'):]: v for k, v in state_dict_schema().items() if k.startswith('vfeat_extractor.')}
         _build_tree(self, schema)
         _init_reference_like(self)
@@ -264,8 +266,28 @@ class MotionFormer(_KernelModule):
         self._tap('v_embed', x, V_TOK)
         M = n * V_TOK
         ln, qkv, att, hid = (ops.empty_bf16((M, w * D), dev) for w in (1, 3, 1, 4))
-        fused = self.fuse_layernorm and ops.GEMM_IMPL != 1          # the CUDA-core bring-up GEMM has no EMIT_LN epilogue
-        if fused:
+        fused = self.fuse_layernorm if ops.GEMM_IMPL != 1 else 0    # the CUDA-core bring-up GEMM has no EMIT_LN epilogue
+        if fused == 2:
+            # norm3 / norm1 fused into the qkv GEMMs (statistics and bf16 copy from the fc2 / time-proj epilogues), norm2 as a LayerNorm launch
+            st0 = torch.empty((M, 1, 2), device=dev, dtype=torch.float32)
+            st = torch.empty((M, D // 64, 2), device=dev, dtype=torch.float32)
+            ops.rowstats_cast(x, ln, st0)
+            cur = st0
+            for i in range(12):
+                b = f'blocks.{i}.'
+                ops.gemm(ln, W[b + 'timeattn.qkv.fold_w'], W[b + 'timeattn.qkv.fold_b'], out=qkv, ln_fold=(cur, W[b + 'timeattn.qkv.fold_cs'], EPS_V))
+                self._divided_attention(qkv, att, n, 'time')
+                ops.gemm(att, W[b + 'timeattn.proj'], P[b + 'timeattn.proj.bias'], out=x, residual=x, out_f32=True, emit_ln=(ln, st))
+                cur = st
+                ops.gemm(ln, W[b + 'attn.qkv.fold_w'], W[b + 'attn.qkv.fold_b'], out=qkv, ln_fold=(st, W[b + 'attn.qkv.fold_cs'], EPS_V))
+                self._divided_attention(qkv, att, n, 'space')
+                ops.gemm(att, W[b + 'attn.proj'], P[b + 'attn.proj.bias'], out=x, residual=x, out_f32=True)
+                ops.layernorm(x, P[b + 'norm2.weight'], P[b + 'norm2.bias'], EPS_V, out=ln)
+                ops.gemm(ln, W[b + 'mlp.fc1'], P[b + 'mlp.fc1.bias'], out=hid, gelu=True)
+                ops.gemm(hid, W[b + 'mlp.fc2'], P[b + 'mlp.fc2.bias'], out=x, residual=x, out_f32=True, emit_ln=(ln, st) if i < 11 else None)
+                if i in (0, 11):
+                    self._tap(f'v_block{i}', x, V_TOK)
+        elif fused:
             # No LayerNorm pass inside the blocks: every residual GEMM (proj / fc2) leaves a bf16 copy of the stream in `ln` plus per-row
             # partial sums in `st`, and the next qkv / fc1 GEMM normalises in its epilogue (folded gamma / beta).
             st0 = torch.empty((M, 1, 2), device=dev, dtype=torch.float32)

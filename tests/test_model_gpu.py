@@ -100,31 +100,35 @@ def test_intermediate_taps_match_reference_golden(model_s2, golden):
     assert model_s2.vfeat_extractor._taps is None
 
 
-def test_fused_layernorm_schedule_matches_golden(model_s2, golden):
-    """The opt-in schedule without LayerNorm launches inside the Motionformer blocks (EMIT_LN / LN_FOLD GEMM epilogues, SFB_LN_FUSED=1)
-    against the reference golden and against the default schedule: same features to bf16 rounding noise."""
+@pytest.mark.parametrize('mode,removed', [(1, 35), (2, 23)])
+def test_fused_layernorm_schedule_matches_golden(model_s2, golden, mode, removed):
+    """The schedules with LayerNorm fused into the GEMMs on either side of it (EMIT_LN / LN_FOLD epilogues): SFB_LN_FUSED=1 (all three norms
+    of a Motionformer block) and 2 (the two norms in front of the qkv GEMMs) against the reference golden and against the schedule with
+    LayerNorm launches: same features to bf16 rounding noise."""
     from synchformer_b200 import ops, synth
     g, _ = golden
     vis = synth.synthetic_video(2, 2, 0).cuda()
     ve = model_s2.vfeat_extractor
+    before = ve.fuse_layernorm
     with torch.no_grad():
-        base = model_s2.extract_vfeats(vis)
-        n0 = ops.launch_count()
-        model_s2.extract_vfeats(vis)
-        launches_default = ops.launch_count() - n0
-        ve.fuse_layernorm = True
         try:
+            ve.fuse_layernorm = 0
+            base = model_s2.extract_vfeats(vis)
+            n0 = ops.launch_count()
+            model_s2.extract_vfeats(vis)
+            launches_default = ops.launch_count() - n0
+            ve.fuse_layernorm = mode
             n0 = ops.launch_count()
             fused = model_s2.extract_vfeats(vis)
             launches_fused = ops.launch_count() - n0
         finally:
-            ve.fuse_layernorm = False
+            ve.fuse_layernorm = before
     torch.cuda.synchronize()
-    assert launches_default - launches_fused == 35                       # 36 LayerNorm launches replaced by one rowstats_cast
+    assert launches_default - launches_fused == removed                  # 36 (24) LayerNorm launches replaced by one rowstats_cast
     assert rel_l2(fused, g['vfeats']) <= FEAT_TOL, rel_l2(fused, g['vfeats'])
     assert rel_l2(fused, base) <= FEAT_TOL
-    print('fused-LayerNorm schedule: vfeats rel-L2 vs golden %.2e (default schedule %.2e), vs default schedule %.2e'
-          % (rel_l2(fused, g['vfeats']), rel_l2(base, g['vfeats']), rel_l2(fused, base)))
+    print('fused-LayerNorm schedule %d: vfeats rel-L2 vs golden %.2e (LayerNorm launches %.2e), vs that schedule %.2e'
+          % (mode, rel_l2(fused, g['vfeats']), rel_l2(base, g['vfeats']), rel_l2(fused, base)))
 
 
 def test_config2_shape_single_clip_matches_oracle(cuda_device):

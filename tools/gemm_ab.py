@@ -53,6 +53,22 @@ def main():
             x.normal_()                                  # the in-place residual adds must not run away
     for c in cases:
         print(f'{c:44s}' + '  '.join(f'{v} {statistics.median(res[c][v]):.3f} ms' for v in VARIANTS))
+    # LN_FOLD consumers next to their plain versions (same interleaving; the statistics / bf16 copy come from the EMIT_LN run above)
+    os.environ['SFB_GEMM_F32_TMA'] = '1'
+    ln = torch.randn(M, D, device=dev).bfloat16()
+    qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
+    ops.gemm(att, wp, bias, out=x, residual=x, out_f32=True, emit_ln=(xb, st))
+    wq = (torch.randn(3 * D, D, device=dev) * 0.02).bfloat16()
+    w1 = (torch.randn(4 * D, D, device=dev) * 0.02).bfloat16()
+    bq, b1 = torch.zeros(3 * D, device=dev), torch.zeros(4 * D, device=dev)
+    csq, cs1 = wq.float().sum(1).contiguous(), w1.float().sum(1).contiguous()
+    pairs = {'qkv': (lambda: ops.gemm(ln, wq, bq, out=qkv), lambda: ops.gemm(xb, wq, bq, out=qkv, ln_fold=(st, csq, 1e-6))),
+             'fc1 + gelu': (lambda: ops.gemm(ln, w1, b1, out=hid, gelu=True), lambda: ops.gemm(xb, w1, b1, out=hid, gelu=True, ln_fold=(st, cs1, 1e-6)))}
+    for name, (plain, fold) in pairs.items():
+        tp, tf = [], []
+        for _ in range(rounds):
+            tp.append(timeit(plain)), tf.append(timeit(fold))
+        print(f'{name:44s}plain {statistics.median(tp):.3f} ms  ln_fold {statistics.median(tf):.3f} ms')
 
 
 if __name__ == '__main__':
