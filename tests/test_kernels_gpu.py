@@ -131,6 +131,43 @@ def test_gemm_layernorm_fusion(cuda_device, impl, M, N, gelu):
     assert rel_l2(y2.float(), ref) < 4e-3
 
 
+@pytest.mark.parametrize('impl', [pytest.param(0, id='auto'), pytest.param(2, id='tc1cta'), pytest.param(3, id='tcpair')])
+@pytest.mark.parametrize('M,N,K', [(1, 768, 768), (77, 40, 72), (300, 96, 256), (129, 1536, 768), (1000, 2304, 768), (257, 264, 64), (4099, 768, 3072)])
+def test_gemm_fp32_epilogues_tails_and_strides(cuda_device, monkeypatch, impl, M, N, K):
+    """fp32-output epilogues (TMA: residual box in / tile out; per-thread: SFB_GEMM_F32_TMA=0) on ragged M / N, with the residual stream
+    updated in place, a residual with its own row stride, a strided output (a column block of a wider matrix, untouched outside), and the
+    broadcast residual row that always takes the per-thread path - each against fp32 torch, and the two epilogues against each other."""
+    from synchformer_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(M * 13 + N)
+    a = _bf(torch.randn(M, K, device='cuda', generator=g))
+    w = _bf(torch.randn(N, K, device='cuda', generator=g) * 0.05)
+    b = torch.randn(N, device='cuda', generator=g)
+    res_wide = torch.randn(M, N + 8, device='cuda', generator=g)
+    res = res_wide[:, :N]                                                   # row stride N + 8
+    lin = a.float() @ w.float().T + b
+    tol = 2.5e-6 * max(1.0, (K / 768) ** 0.5)                               # fp32 accumulation in a different order than torch's
+    outs = {}
+    for tma in ('1', '0'):
+        monkeypatch.setenv('SFB_GEMM_F32_TMA', tma)
+        plain = ops.gemm(a, w, b, out_f32=True, impl=impl)
+        assert rel_l2(plain, lin) < tol
+        with_res = ops.gemm(a, w, b, residual=res, out_f32=True, impl=impl)
+        assert rel_l2(with_res, lin + res) < tol
+        x = res.contiguous().clone()
+        ops.gemm(a, w, b, out=x, residual=x, out_f32=True, impl=impl)          # in place on the stream
+        assert rel_l2(x, lin + res) < tol
+        wide = torch.full((M, N + 16), 7.0, device='cuda')
+        ops.gemm(a, w, None, out=wide[:, 8:8 + N], residual=res, out_f32=True, gelu=True, impl=impl)
+        assert rel_l2(wide[:, 8:8 + N], torch.nn.functional.gelu(lin - b) + res) < 2 * tol
+        assert float((wide[:, :8] - 7.0).abs().max()) == 0.0 and float((wide[:, 8 + N:] - 7.0).abs().max()) == 0.0
+        bc = ops.gemm(a, w, b, residual=res[:1].contiguous(), out_f32=True, impl=impl)
+        assert rel_l2(bc, lin + res[:1]) < tol
+        outs[tma] = (plain, with_res, x)
+    torch.cuda.synchronize()
+    for u, v in zip(outs['1'], outs['0']):
+        assert torch.equal(u, v)                                              # same accumulator, same fp32 additions in the same order
+
+
 def test_gemm_full_size_linearity_property(cuda_device):
     """At the benchmark's row count (64 clips x 8 segments x 1569 tokens) the result cannot be compared with a CPU oracle in
     seconds; use linearity instead: (A + A') W == A W + A' W up to fp32 accumulation order, on a strided sample of rows."""
