@@ -19,7 +19,7 @@
 // [0,64) as the softmax consumes S, P of keys 128..207 goes to the spare columns [208,248), O accumulates in columns [64,128).
 // Nothing touches HBM between the qkv activations and the attention output.
 //
-// What bounds it (round 2, clock64 phase stamps of one CTA, tools/attn_pipe.py; 1.76 -> 1.09 ms per launch at 512 segments):
+// What bounds it (round 2, clock64 phase stamps of one CTA, tools/attn_pipe.py; 1.76 -> 1.06 ms per launch at 512 segments):
 //   * the MMA phases are short bursts whose cost is issue + ~400 clocks of commit latency, not tensor work: fully unrolled issue sequences
 //     with constant-offset descriptors (56 instead of 150 clocks per tcgen05.mma, tools/ubench/mma_cost.cu);
 //   * the two tiles of a problem must not run in lock-step: issue order S(0,i) PV(1,i-1) S(1,i) PV(0,i) puts one tile's exp2 pass (XU
@@ -32,10 +32,9 @@
 //     Lk >= 192 and the chunk loops are rolled (89 KB -> 58 KB of SASS: 1.37 -> 1.19 ms on its own).
 //   * the loads of problem i+1 must not wait for the last P V of problem i-1: Q / K and V of a stage are handed back on separate barriers
 //     (Q and K are dead once both S tiles exist), 1.19 -> 1.13 ms;
-//   * softmax in ONE sweep over TMEM (reference value = maximum of the first 32 scores, the true maximum tracked beside the exp2s, rows
-//     that rise more than 2^100 above their reference flagged and recomputed by attn_space_fixup_kernel) and the first 8 of the 13 P V
-//     instructions issued while the scores of keys 128.. are still being exponentiated (P / O laid out so that O never overlaps live
-//     scores): 1.13 -> 1.09 ms.  What is left is the XU pipe: 2 x 32 rows x 208 exp2 per sub-partition and problem at ~10.5 clocks per
+//   * softmax in ONE sweep over TMEM (reference value = maximum of the first 32 scores; a row whose sum of 2^(score - reference) reaches
+//     2^110 is flagged and recomputed by attn_space_fixup_kernel) and the first 8 of the 13 P V instructions issued while the scores of
+//     keys 128.. are still being exponentiated (P / O laid out so that O never overlaps live scores): 1.13 -> 1.06 ms.  What is left is the XU pipe: 2 x 32 rows x 208 exp2 per sub-partition and problem at ~10.5 clocks per
 //     MUFU.EX2 warp instruction (tools/ubench/xu_pipe.cu) = 4 400 of the ~5 800 clocks of a problem.
 // Tried and measured, not adopted: a single-pass softmax whose reference value is the Cauchy-Schwarz bound |q| max|k| scale (the norms from
 // shared memory plus a named barrier cost 30 %); a lazily raised reference with an in-line rescale branch per chunk (drains the XU pipe at
@@ -73,7 +72,7 @@ constexpr uint32_t SMEM_TC = 2 * STAGE_BYTES_TC + 2 * O_STAGE_BYTES + 1024;
 // the softmax is still reading the scores of keys 128.. from columns [128,208)
 constexpr uint32_t TILE_COLS = 256, P_COL = 0, PB_COL = 208, O_COL = 64;
 constexpr int kKeysA = 128;              // keys covered by the first P V burst
-constexpr float kMaxAboveRef = 100.f;   // single-pass softmax: how far (log2) a row's maximum may lie above its reference value
+constexpr float kSumLimit = 1.2980742e33f;   // 2^110: single-pass softmax, a row whose sum of 2^(score - reference) reaches this is recomputed
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -397,14 +396,15 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 // ---- ONE pass over the scores: p = 2^(s*scale*log2e - ref), row sum, P (bf16 pairs) written over the already consumed S
                 // columns.  `ref` is not the row maximum - finding that first is a second sweep over TMEM, 980 of the 6 000 clocks of a
                 // problem - but the maximum of the first 32 scores.  Softmax is invariant to the reference as long as nothing overflows,
-                // so the true maximum is formed NEXT TO the exp2s (FMNMX3s, hidden under the XU-bound exp2s; no branch, nothing waits for
-                // them) and examined afterwards: a row whose maximum exceeds its reference by less than 2^100 has P <= 2^100 and an fp32
-                // row sum <= 208 * 2^100 - exact, and >= 1 because the reference is one of the row's own scores.  A row beyond that (never
-                // seen outside the adversarial unit test) is reported in `flags` and recomputed by attn_space_fixup_kernel afterwards.
-                float sum = 0.f, run;
+                // and whether anything came close is visible in the row sum afterwards: sum < 2^110 means every p < 2^110 (bf16 P, the
+                // fp32 sum and the fp32 O accumulators are all far from overflow; the sum is >= 1 because the reference is one of the row's
+                // own scores), so the row is exact.  A row beyond that (a score more than ~100 log2 units above the first 32; never seen
+                // outside the adversarial unit test) is reported in `flags` and recomputed by attn_space_fixup_kernel afterwards.
+                float sum = 0.f;
                 uint32_t pk[16];
                 tmem_ld32(trow, ra);
                 tmem_ld_wait_dep(ra);
+                float mxs;
                 {
                     float m0 = -INFINITY;
                     if (kFull192 || 32 <= d.Lk) softmax_max32(ra, m0);
@@ -412,9 +412,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (j < lk) m0 = fmaxf(m0, __uint_as_float(ra[j]));
                     }
-                    run = m0;
+                    mxs = m0 * sl2;
                 }
-                const float mxs = run * sl2;
                 if ((warp & 3) == 0) SFB_TS(7 + 8 * t);
 #pragma unroll 1          // rolled: the softmax loop body has to stay inside the instruction cache (see the header)
                 for (int c = 0; c < 6; c += 2) {
@@ -432,17 +431,12 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     tmem_ld_wait_dep(rb);
                     tmem_st16(trow + (c < 4 ? P_COL + c * 16 : PB_COL + (c - 4) * 16), pk);
                     if (c + 2 < 6) tmem_ld32(trow + (c + 2) * 32, ra); else tmem_ld16_into32(trow + 192, ra);
-                    if (kFull192 || (c + 2) * 32 <= d.Lk) {
-                        softmax_max32(rb, run);
-                        softmax_exp32(rb, pk, sl2, mxs, sum);
-                    } else {
+                    if (kFull192 || (c + 2) * 32 <= d.Lk) softmax_exp32(rb, pk, sl2, mxs, sum);
+                    else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const bool l0 = (c + 1) * 32 + j < lk, l1 = (c + 1) * 32 + j + 1 < lk;
-                            if (l0) run = fmaxf(run, __uint_as_float(rb[j]));
-                            if (l1) run = fmaxf(run, __uint_as_float(rb[j + 1]));
-                            const float p0 = l0 ? ex2f(fmaf(__uint_as_float(rb[j]), sl2, -mxs)) : 0.f;
-                            const float p1 = l1 ? ex2f(fmaf(__uint_as_float(rb[j + 1]), sl2, -mxs)) : 0.f;
+                            const float p0 = (c + 1) * 32 + j < lk ? ex2f(fmaf(__uint_as_float(rb[j]), sl2, -mxs)) : 0.f;
+                            const float p1 = (c + 1) * 32 + j + 1 < lk ? ex2f(fmaf(__uint_as_float(rb[j + 1]), sl2, -mxs)) : 0.f;
                             sum += p0 + p1;
                             pk[j >> 1] = pack_bf16x2(p0, p1);
                         }
@@ -455,33 +449,19 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                         __syncwarp();
                         if (lane == 0) mbar_arrive(p_bar(t));
                     }
-                    // the chunk now in `ra` (32 columns, or the 16-column tail after the last round) joins the running maximum
-                    if (c + 2 < 6) {
-                        if (kFull192 || (c + 3) * 32 <= d.Lk) softmax_max32(ra, run);
-                        else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if ((c + 2) * 32 + j < lk) run = fmaxf(run, __uint_as_float(ra[j]));
-                        }
-                    }
                 }
                 {
                     uint32_t pt[8];
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
-                        const bool l0 = 192 + j < lk, l1 = 192 + j + 1 < lk;
-                        if (l0) run = fmaxf(run, __uint_as_float(ra[j]));
-                        if (l1) run = fmaxf(run, __uint_as_float(ra[j + 1]));
-                        const float p0 = l0 ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
-                        const float p1 = l1 ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
+                        const float p0 = 192 + j < lk ? ex2f(fmaf(__uint_as_float(ra[j]), sl2, -mxs)) : 0.f;
+                        const float p1 = 192 + j + 1 < lk ? ex2f(fmaf(__uint_as_float(ra[j + 1]), sl2, -mxs)) : 0.f;
                         sum += p0 + p1;
                         pt[j >> 1] = pack_bf16x2(p0, p1);
                     }
                     tmem_st8(trow + PB_COL + 32, pt);
                 }
-                {   // rows with infinite / NaN scores are left alone: they come out non-finite either way, as in the reference
-                    const float over = fmaf(run, sl2, -mxs);
-                    redo = over > kMaxAboveRef && over < INFINITY;
-                }
+                redo = sum >= kSumLimit;         // +inf included; NaN rows (non-finite inputs) are left alone: they come out non-finite either way, as in the reference
                 tmem_st_wait();
                 inv = 1.0f / sum;
                 mxs_keep = mxs, sum_keep = sum;
@@ -579,7 +559,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 }
 
 
-// Rows the single-pass softmax reported in `flags` (their scores rise more than 2^kMaxAboveRef above the first 32 scores): recomputed from
+// Rows the single-pass softmax reported in `flags` (a score more than ~100 log2 units above the first 32 scores: row sum >= kSumLimit): recomputed from
 // the operands in global memory with an online softmax, one warp per row, and written over what the tensor-core kernel stored - the
 // output row, or the partial state of the fused extra query (which the merge kernel reads afterwards).  Word w of a problem's 8 flag words
 // covers query rows 32 w .. 32 w + 31.  With no row reported (always, outside the unit test) this kernel reads 32 bytes per problem.
