@@ -457,16 +457,18 @@ __global__ void __launch_bounds__(HD == 64 ? 512 : 416) attn_mma_kernel(const De
 
 // --------------------------------------------------------------- Motionformer time attention on tensor cores
 // Lq = Lk = 8 frames + CLS prefix key, hd 64.  One CTA handles one PAIR of spatial locations for all heads (one warp per head,
-// two CTAs per SM so one loads while the other computes): the 16 x (3 * n_heads * 64) tile [2 locations x 8 frames] x [q | k | v] is
+// THREE CTAs per SM so that loads, math and stores of different pairs overlap: 56 registers per thread and exactly 75 KB of shared memory -
+// the rows are 128B-swizzled (16-byte chunk ^ (row & 7)) instead of padded, which is what makes the third CTA fit): the
+// 16 x (3 * n_heads * 64) tile [2 locations x 8 frames] x [q | k | v] is
 // staged with cp.async (fully coalesced 1.5 KB row pieces), and the two 8 x 9 attentions of a pair are evaluated as ONE block-
 // diagonal m16n8k16 problem: S = [Q_a; Q_b] [K_a | K_b | k_cls]^T keeps the two diagonal 8 x 8 blocks and the CLS column,
 // O = P V with P zero off the diagonal blocks.  28 mma.sync per (pair, head) instead of 2 x 9 x 64 x 2 x 8 CUDA-core FMAs.
 template <int H, bool kExtra = false>   // heads == warps per CTA; kExtra: also serve the fused extra (CLS) query, see the end of the kernel
-__global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) {
+__global__ void __launch_bounds__(H * 32, 3) attn_time_mma_kernel(const Desc d) {
     constexpr int HD = 64;
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int seg_bytes = H * HD * 2;             // one of q / k / v for one token, all heads
-    constexpr int PITCH = 3 * seg_bytes + 16;         // +16: ldmatrix rows land on distinct bank groups
+    constexpr int PITCH = 3 * seg_bytes;              // no padding: chunk c of row r is stored at chunk c ^ (r & 7), so ldmatrix rows land on distinct bank groups
     constexpr int cls_off = 16 * PITCH;               // [k_cls | v_cls] of the segment
     constexpr int chunks_seg = seg_bytes / 16;
     const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
@@ -491,7 +493,8 @@ __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) 
             src = (sgm == 48 ? d.kp : d.vp) + o * d.prefix_outer;
             dst = s0 + cls_off + (sgm - 48) * seg_bytes;
         }
-        for (int cc = lane; cc < chunks_seg; cc += 32) cp_async16(dst + cc * 16, src + cc * 8);
+        const int swz = sgm < 48 ? ((sgm / 3) & 7) : 0;             // the CLS segments are read as one broadcast row: not swizzled
+        for (int cc = lane; cc < chunks_seg; cc += 32) cp_async16(dst + ((cc ^ swz) << 4), src + cc * 8);
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -507,8 +510,8 @@ __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) 
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 uint32_t a0, a1, a2, a3, b0, b1, b2, b3, c0, c1;
-                ldmatrix_x4(hq + (lane & 15) * PITCH + (lane >> 4) * 16 + ks * 32, a0, a1, a2, a3);
-                ldmatrix_x4(hk + ((lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 16 + ks * 32, b0, b1, b2, b3);
+                ldmatrix_x4(hq + (lane & 15) * PITCH + ((((lane >> 4) + ks * 2) ^ (lane & 7)) << 4), a0, a1, a2, a3);
+                ldmatrix_x4(hk + ((lane & 7) + ((lane >> 4) << 3)) * PITCH + (((((lane >> 3) & 1) + ks * 2) ^ (lane & 7)) << 4), b0, b1, b2, b3);
                 // CLS key: every row address of the 8 x 8 matrices points at the single k_cls row (columns 1..7 are duplicates, ignored)
                 asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(c0), "=r"(c1) : "r"(ck + ((lane >> 3) & 1) * 16 + ks * 32));
                 mma_bf16_16816(s[0], a0, a1, a2, a3, b0, b1);     // x keys of location a: rows 0-7 valid
@@ -541,7 +544,7 @@ __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) 
 #pragma unroll
             for (int n2 = 0; n2 < 4; ++n2) {
                 uint32_t b0, b1, b2, b3;
-                ldmatrix_x4_trans(hv + ((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16 + n2 * 32, b0, b1, b2, b3);
+                ldmatrix_x4_trans(hv + ((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + ((((lane >> 4) + n2 * 2) ^ (lane & 7)) << 4), b0, b1, b2, b3);
                 mma_bf16_16816(oacc[2 * n2], pa0, 0u, 0u, pa3, b0, b1);
                 mma_bf16_16816(oacc[2 * n2 + 1], pa0, 0u, 0u, pa3, b2, b3);
                 // CLS value: all 16 "key" rows of this k16 step point at v_cls (finite), only key 0 has a non-zero probability
@@ -554,8 +557,8 @@ __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) 
             uint8_t *so = smem + warp * (HD * 2);
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                *reinterpret_cast<uint32_t *>(so + g * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][0], oacc[n][1]);
-                *reinterpret_cast<uint32_t *>(so + (g + 8) * PITCH + n * 16 + t4 * 4) = pack_bf16x2(oacc[n][2], oacc[n][3]);
+                *reinterpret_cast<uint32_t *>(so + g * PITCH + ((n ^ g) << 4) + t4 * 4) = pack_bf16x2(oacc[n][0], oacc[n][1]);
+                *reinterpret_cast<uint32_t *>(so + (g + 8) * PITCH + ((n ^ g) << 4) + t4 * 4) = pack_bf16x2(oacc[n][2], oacc[n][3]);
             }
             __syncwarp();
             __nv_bfloat16 *og = d.out + o * d.o_outer + warp * HD;
@@ -563,7 +566,7 @@ __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) 
             for (int c = lane; c < 16 * 8; c += 32) {
                 const int r = c >> 3, cc = c & 7;
                 *reinterpret_cast<uint4 *>(og + static_cast<int64_t>(i0p + (r >> 3)) * d.o_inner + static_cast<int64_t>(r & 7) * d.o_row + cc * 8) =
-                    *reinterpret_cast<const uint4 *>(so + r * PITCH + cc * 16);
+                    *reinterpret_cast<const uint4 *>(so + r * PITCH + ((cc ^ (r & 7)) << 4));
             }
         }
     }
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) 
         const uint8_t *kcls = smem + cls_off + warp * (HD * 2), *vcls = kcls + seg_bytes;
         float sc = 0.f;
         for (int j = 0; j < 17; ++j) {
-            const float2 kk = unpack_bf16x2(*reinterpret_cast<const uint32_t *>((j < 16 ? kbase + j * PITCH : kcls) + lane * 4));
+            const float2 kk = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(j < 16 ? kbase + j * PITCH + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4 : kcls + lane * 4));
             const float p = warp_sum(qx.x * kk.x + qx.y * kk.y);
             if (lane == j) sc = p * sl2;
         }
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(H * 32, 2) attn_time_mma_kernel(const Desc d) 
         float2 oa = make_float2(0.f, 0.f), ob = make_float2(0.f, 0.f);
         for (int j = 0; j < 17; ++j) {
             const float wa = __shfl_sync(0xffffffffu, pa, j), wb = __shfl_sync(0xffffffffu, pb, j);
-            const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t *>((j < 16 ? vbase + j * PITCH : vcls) + lane * 4));
+            const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(j < 16 ? vbase + j * PITCH + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4 : vcls + lane * 4));
             oa.x = fmaf(wa, vv.x, oa.x), oa.y = fmaf(wa, vv.y, oa.y);
             ob.x = fmaf(wb, vv.x, ob.x), ob.y = fmaf(wb, vv.y, ob.y);
         }
@@ -740,7 +743,7 @@ extern "C" int sfb_attention(const sfb_attn_desc *desc, void *stream) {
     if (desc->impl == 0 && aligned16 && HD == 64 && d.Lq == 8 && d.Lk == 8 && d.has_prefix && d.n_inner % 2 == 0 && d.n_heads == 12) {
         constexpr int H = 12;
         constexpr int seg_bytes = H * 64 * 2;
-        constexpr int smem_bytes = 16 * (3 * seg_bytes + 16) + 2 * seg_bytes + 16;       // 77 KB: two CTAs per SM
+        constexpr int smem_bytes = 16 * 3 * seg_bytes + 2 * seg_bytes;                   // exactly 75 KB: three CTAs per SM (3 x (75 + 1) KB = 228 KB)
         static PerDeviceOnce attr_once;
         if (attr_once.first()) {
             SFB_CHECK_CUDA(cudaFuncSetAttribute(attn_time_mma_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
