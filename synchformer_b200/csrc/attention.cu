@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) attn_time_kernel(const Desc d) {
 // load instruction covers 4 rows x 128 contiguous bytes), the 32 lane-groups of the CTA stride over the keys with a private
 // online softmax (3 shuffles per key), K and V of 4 keys in flight per lane, and the 32 partial (max, sum, acc) states are
 // merged through shared memory.  One pass over K and V: HBM-bound at large batch, latency-tolerant at small batch.
-__global__ void __launch_bounds__(256) attn_row1_kernel(const Desc d) {
+__global__ void __launch_bounds__(256, 4) attn_row1_kernel(const Desc d) {
     constexpr int HD = 64, G = 32;           // lane groups per CTA
     __shared__ float s_m[G], s_l[G];
     __shared__ float s_acc[G][HD + 4];
